@@ -1,0 +1,175 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python drivers.
+
+Run in the build container only (needs /root/reference, read-only):
+
+    python tests/golden/make_golden.py
+
+What is real and what is stubbed:
+  * REAL: /root/reference/python_scripts/halo_gas.py (RPS, most_bound_particle,
+    brute_force_binding_energy_fortran) and halo_properties.py
+    (escape_velocity_unbinding_fortran, center_of_mass, CM_velocity, total_mass) are
+    imported and executed unmodified.
+  * STUB: `masclet_framework` and `matplotlib` (absent, un-vendored; only imported at
+    module top, and `units.mass_to_sun` = 1 so DM masses are already in Msun), and
+    `halo_gas.AMRgrid_to_particles` (needs MASCLET AMR files) which is
+    replaced by a function returning the synthetic gas particles.
+  * ORACLE: `fortran_modules.particle` -- the f2py module that cannot be built here (no
+    Fortran compiler) -- is bound to oracle/oracle.py's C restatement.  Every kernel call
+    is recorded, so the fixtures also pin the order and sizes of the calls.
+
+The fixtures therefore pin the reference's driver semantics (class order, dtype
+promotions, energy step, mask, mass sums, argmin, sampling RNG use) around the kernel;
+the kernel arithmetic itself stays "parity unpinned" (see oracle/halma_oracle.c).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import oracle as O  # noqa: E402
+from pyhalma_b200 import synth  # noqa: E402
+
+CALLS = []
+
+
+class _RecordingParticle:
+    @staticmethod
+    def brute_force_binding_energy(ncores, ntotal, tm, tx, ty, tz, ntest, sx, sy, sz):
+        out = O.brute_force_binding_energy(ncores, ntotal, tm, tx, ty, tz, ntest, sx, sy, sz)
+        CALLS.append((int(ntotal), int(ntest), out.copy()))
+        return out
+
+    @staticmethod
+    def serial_brute_force_binding_energy(ntotal, tm, tx, ty, tz, ntest, sx, sy, sz):
+        out = O.serial_brute_force_binding_energy(ntotal, tm, tx, ty, tz, ntest, sx, sy, sz)
+        CALLS.append((int(ntotal), int(ntest), out.copy()))
+        return out
+
+
+def install_stubs():
+    mf = types.ModuleType("masclet_framework")
+    for sub in ("units", "tools", "particles", "particle2grid"):
+        m = types.ModuleType("masclet_framework." + sub)
+        setattr(mf, sub, m)
+        sys.modules["masclet_framework." + sub] = m
+    mf.units.mass_to_sun = 1.0
+    sys.modules["masclet_framework"] = mf
+    mpl = types.ModuleType("matplotlib")
+    plt = types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pyplot"] = plt
+    fm = types.ModuleType("fortran_modules")
+    fm.__path__ = []
+    part = types.ModuleType("fortran_modules.particle")
+    part.particle = _RecordingParticle
+    fm.particle = part
+    sys.modules["fortran_modules"] = fm
+    sys.modules["fortran_modules.particle"] = part
+    sys.path.insert(0, REF)
+
+
+def pack_calls():
+    d = {"n_calls": np.int64(len(CALLS))}
+    for k, (nt, ns, out) in enumerate(CALLS):
+        d["call%d_ntotal" % k] = np.int64(nt)
+        d["call%d_ntest" % k] = np.int64(ns)
+        d["call%d_be" % k] = out
+    CALLS.clear()
+    return d
+
+
+def small_case(seed, two_species, dm_mass=8e7 / 8):
+    rng = np.random.default_rng(seed)
+    stars = synth.plummer_stars(260, 2 * synth.KPC, 1e6, rng)
+    synth.add_coincident_pairs(stars, 3, rng)
+    gas = synth.lattice_gas(420, synth.CELL, rng, m_total=6e7)
+    dm = synth.dm_cloud(310, 5 * synth.KPC, dm_mass, rng, two_species=two_species)
+    return stars, gas, dm
+
+
+def inputs_dict(stars, gas, dm):
+    d = {}
+    for name, p, keys in (("st", stars, ("x", "y", "z", "vx", "vy", "vz", "mass")),
+                          ("gas", gas, ("x", "y", "z", "vx", "vy", "vz", "mass", "temp")),
+                          ("dm", dm, ("x", "y", "z", "mass"))):
+        for k in keys:
+            d["%s_%s" % (name, k)] = getattr(p, k)
+    return d
+
+
+def main():
+    install_stubs()
+    from python_scripts import halo_gas, halo_properties  # the reference, unmodified
+
+    mass_dm_part = 8e7
+    for tag, two_species, lim, seed in (("rps_one_dm", False, 5000, 11),
+                                        ("rps_two_dm", True, 5000, 12),
+                                        ("rps_sampled", True, 100, 13)):
+        stars, gas, dm = small_case(seed, two_species)
+        part_list = np.arange(len(stars))
+        cx, cy, cz, M = halo_properties.center_of_mass(part_list, stars.x, stars.y, stars.z, stars.mass)
+        vb = halo_properties.CM_velocity(M, part_list, stars.vx, stars.vy, stars.vz, stars.mass)
+        num_dm_species = 2 if two_species else 1
+        np.random.seed(4242)
+        out = halo_gas.RPS(gas.x, gas.y, gas.z, gas.vx, gas.vy, gas.vz, gas.mass, gas.temp,
+                           dm.x, dm.y, dm.z, dm.mass, stars.x, stars.y, stars.z, stars.mass,
+                           vb[0], vb[1], vb[2], lim, mass_dm_part, num_dm_species)
+        d = inputs_dict(stars, gas, dm)
+        d.update(pack_calls())
+        d.update(rps_out=np.array(out, dtype=np.float64), vb=np.array(vb), com=np.array([cx, cy, cz]),
+                 M=np.float64(M), lim=np.int64(lim), mass_dm_part=np.float64(mass_dm_part),
+                 num_dm_species=np.int64(num_dm_species), np_seed=np.int64(4242))
+        np.random.seed(4242)
+        mb = halo_gas.most_bound_particle(gas.x, gas.y, gas.z, gas.mass, dm.x, dm.y, dm.z, dm.mass,
+                                          stars.x, stars.y, stars.z, stars.mass,
+                                          np.arange(len(stars)) + 1000, lim, mass_dm_part)
+        mbc = pack_calls()
+        d.update({"mb_" + k: v for k, v in mbc.items()})
+        d.update(mb_out=np.array(mb, dtype=np.float64))
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), **d)
+        print(tag, "RPS ->", out, " most_bound ->", mb)
+
+    # stellar one-pass unbinding, halo_properties.py:282-361
+    stars, gas, dm = small_case(21, False, dm_mass=8e7 / 512)   # light DM: mixed bound/unbound mask
+    rete, rho_B, Rmax, factor_v = 0.8, 1.0, 1.0, 3.0
+    # :326 multiplies the gathered gas mass by rete**3 in place: hand it mass / rete**3
+    gas_mass_pre = gas.mass / rete ** 3
+    halo_gas.AMRgrid_to_particles = lambda L, ncoarse, grid_data, gas_data, R, cx, cy, cz, rho: (
+        gas.x.copy(), gas.y.copy(), gas.z.copy(), None, None, None, gas_mass_pre.copy(), None)
+    # global star arrays larger than the halo, gathered through part_list (:302-308)
+    rng = np.random.default_rng(5)
+    n_glob = 400
+    part_list = np.sort(rng.choice(n_glob, len(stars), replace=False))
+    glob = {k: rng.normal(0, 1, n_glob) for k in ("x", "y", "z", "vx", "vy", "vz", "mass")}
+    for k in glob:
+        glob[k][part_list] = getattr(stars, k)
+    cx, cy, cz, M = halo_properties.center_of_mass(part_list, glob["x"], glob["y"], glob["z"], glob["mass"])
+    vb = halo_properties.CM_velocity(M, part_list, glob["vx"], glob["vy"], glob["vz"], glob["mass"])
+    # DM further than Rmax is dropped at :289-299: add two far particles that must be ignored
+    dmx = np.concatenate((dm.x, [cx + 5.0, cx - 7.0]))
+    dmy = np.concatenate((dm.y, [cy, cy]))
+    dmz = np.concatenate((dm.z, [cz, cz]))
+    dmm = np.concatenate((dm.mass, [1e15, 1e15]))
+    bound = halo_properties.escape_velocity_unbinding_fortran(
+        rete, 40.0, 128, None, None, (dmx, dmy, dmz, dmm), cx, cy, cz, vb[0], vb[1], vb[2], Rmax,
+        part_list, glob["x"], glob["y"], glob["z"], glob["vx"], glob["vy"], glob["vz"], glob["mass"],
+        factor_v, rho_B)
+    d = inputs_dict(stars, gas, dm)
+    d.update(pack_calls())
+    # the gas mass the kernel actually saw (after the in-place rete**3 scaling at :326)
+    d["gas_mass_seen"] = gas_mass_pre * rete ** 3
+    d.update(bound=np.asarray(bound), vb=np.array(vb), com=np.array([cx, cy, cz]), M=np.float64(M),
+             factor_v=np.float64(factor_v), part_list=part_list)
+    np.savez_compressed(os.path.join(HERE, "stellar_onepass.npz"), **d)
+    print("stellar_onepass bound", int(np.sum(bound)), "of", len(bound))
+
+
+if __name__ == "__main__":
+    main()
