@@ -1,0 +1,206 @@
+/*
+ * halma_unbind.h -- C-ABI of libhalma_unbind.so, the B200 (sm_100a) replacement for
+ * pyHALMA's direct-sum potential / unbinding hot path.
+ *
+ * Plain C: pointers and sizes only, no torch or C++ types.  Every entry point returns
+ * HALMA_OK (0) or a negative HALMA_ERR_* code (CUDA failures are reported as
+ * HALMA_ERR_CUDA with the text in halma_last_error()).  There is no CPU fallback: a
+ * call on a machine without a usable CUDA device fails with HALMA_ERR_NO_DEVICE.
+ *
+ * Reference interfaces replaced (paths relative to the pyHALMA checkout):
+ *   halma_potential_f32        fortran_modules/particle_subroutines.f90:466-514
+ *                              (brute_force_binding_energy) and :517-556 (serial twin),
+ *                              reached through python_scripts/halo_gas.py:182,208.
+ *   halma_plan_* / halma_unbind_*   the per-halo drivers around that kernel:
+ *                              python_scripts/halo_properties.py:333-361 (stellar
+ *                              energy step and mask), python_scripts/halo_gas.py:299-492
+ *                              (gas classes, energy step, mask, mass sums) and
+ *                              halo_properties.py:16-60 (mass, centre of mass, bulk
+ *                              velocity), iterated to a fixed point.
+ *
+ * Units are the reference's: comoving Mpc, Msun, km/s.
+ */
+#ifndef HALMA_UNBIND_H
+#define HALMA_UNBIND_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HALMA_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define HALMA_OK                0
+#define HALMA_ERR_INVALID      -1   /* bad argument (null pointer, negative size, bad enum) */
+#define HALMA_ERR_NO_DEVICE    -2   /* no CUDA device / device index out of range          */
+#define HALMA_ERR_CUDA         -3   /* CUDA runtime error, see halma_last_error()          */
+#define HALMA_ERR_ALIGN        -4   /* device pointer not 16-byte aligned                  */
+#define HALMA_ERR_TOO_LARGE    -5   /* more than 2^31-16 particles in one call             */
+#define HALMA_ERR_STATE        -6   /* call order violated (e.g. run before upload)        */
+#define HALMA_ERR_NCCL         -7   /* NCCL could not be loaded or a collective failed     */
+
+/* ---- arithmetic modes --------------------------------------------------------------- *
+ * EXACT: bit-faithful to the reference kernel: per pair IEEE sqrt and divide, the
+ *        coordinate-inequality predicate on the float32 inputs, r^2 contracted as
+ *        fma(dz,dz, fma(dx,dx, dy*dy)) (what GCC emits for compile-f2py:4), one float32
+ *        accumulator per target summed in ascending source order; source classes are
+ *        added in float32 in class order (halo_gas.py:301-450).
+ * FAST:  same predicate and per-pair formula with rsqrt.approx, float32 partial sums
+ *        over at most 32 sources flushed into a float64 accumulator; the result is
+ *        rounded once to float32.  Agrees with a float64-accumulating evaluation of the
+ *        reference terms to better than 1e-6 relative.                                   */
+#define HALMA_MODE_FAST   0
+#define HALMA_MODE_EXACT  1
+
+const char *halma_last_error(void);
+int halma_abi_version(void);
+int halma_device_count(int *count);
+/* name[0..len) receives the device name; sm_count / clock_khz may be null. */
+int halma_device_info(int device, char *name, int len, int *sm_count, int *clock_khz,
+                      int64_t *mem_bytes);
+
+/* Pinned host memory for callers that want fast host<->device copies. */
+int halma_host_alloc(void **ptr, int64_t bytes);
+int halma_host_free(void *ptr);
+
+/* ------------------------------------------------------------------------------------ *
+ * brute_force_binding_energy: out_be[i] = sum_j m_j / |r_j - r_i| over the sources whose
+ * x, y AND z all differ from the target's (particle_subroutines.f90:497-510).  Positive,
+ * Msun/Mpc, no G, no softening.  HOST pointers; float32 like the f2py signature.
+ * n_tgt == 0 is a no-op (the wrapper at halo_gas.py:169 never reaches Fortran either).
+ * ------------------------------------------------------------------------------------ */
+int halma_potential_f32(int device, int mode,
+                        const float *src_m, const float *src_x, const float *src_y,
+                        const float *src_z, int64_t n_src,
+                        const float *tgt_x, const float *tgt_y, const float *tgt_z,
+                        int64_t n_tgt, float *out_be);
+
+/* Same with DEVICE pointers (16-byte aligned) on `stream` (a cudaStream_t, 0 = default);
+ * asynchronous.  workspace: device scratch of halma_potential_workspace_bytes(). */
+int64_t halma_potential_workspace_bytes(int64_t n_src, int64_t n_tgt);
+int halma_potential_f32_dev(int device, int mode,
+                            const float *src_m, const float *src_x, const float *src_y,
+                            const float *src_z, int64_t n_src,
+                            const float *tgt_x, const float *tgt_y, const float *tgt_z,
+                            int64_t n_tgt, float *out_be, void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * Unbinding plans.  A plan owns the device-resident state of a batch ("catalogue") of
+ * haloes: members (targets that are also sources) concatenated with CSR `offsets`, and
+ * up to HALMA_MAX_GROUPS groups of fixed external sources, each with its own CSR
+ * offsets over the same haloes.
+ *
+ * Source order / classes per halo:
+ *   split_classes = 0 (stellar, halo_properties.py:333-339): one in-order sum over
+ *       ext group 0 .. n_pre-1, members, ext group n_pre .. n_groups-1.
+ *   split_classes = 1 (gas, halo_gas.py:301-450): members first, then each ext group,
+ *       every class summed on its own and the class sums added in float32 in that order
+ *       (n_pre must be 0).
+ * Energy and mask per pass (halo_properties.py:342-359 / halo_gas.py:456-476):
+ *       pe = -(float)Phi; pe *= (float)G; pe *= (float)kappa        (float32)
+ *       E  = 0.5*((vx-vbx)^2 + (vy-vby)^2 + (vz-vbz)^2) + pe        (float64)
+ *       bound = E <= 0
+ * Iteration: members <- bound members (stable order); unless vb_fixed,
+ * vb <- sum(m v)/sum(m) over the new members (halo_properties.py:45-60); repeat until
+ * the member count stops changing, the set is empty, or max_iter passes were made.
+ * max_iter = 1 with vb_fixed = 1 is exactly the reference's one-pass function.
+ * ------------------------------------------------------------------------------------ */
+#define HALMA_MAX_GROUPS 4
+
+typedef struct halma_plan halma_plan;
+
+typedef struct halma_unbind_config {
+    int32_t struct_size;     /* sizeof(halma_unbind_config), for ABI checks              */
+    int32_t device;
+    int32_t mode;            /* HALMA_MODE_*                                             */
+    int32_t n_groups;        /* external source groups, 0..HALMA_MAX_GROUPS              */
+    int32_t n_pre;           /* groups summed before the members (split_classes = 0)     */
+    int32_t split_classes;   /* 0 stellar layout, 1 gas layout                           */
+    int32_t vb_fixed;        /* 1: bulk velocity given per halo and held fixed           */
+    int32_t max_iter;        /* >= 1                                                     */
+    double  G;               /* 4.3e-9 (km/s)^2 Mpc/Msun; cast to float32 like numpy     */
+    double  kappa;           /* factor_v**2 (stars) or 2.0 (gas); cast to float32        */
+    int32_t rank;            /* split mode: this process's rank ...                      */
+    int32_t n_ranks;         /* ... of n_ranks sharing ONE halo by target groups (1 = off) */
+    int32_t use_graph;       /* 1: run the loop as a CUDA graph with a device-side WHILE  */
+    int32_t reserved;
+} halma_unbind_config;
+
+typedef struct halma_halo_result {
+    int64_t n_bound;         /* members left                                             */
+    int32_t n_iter;          /* potential passes made                                    */
+    int32_t converged;       /* 1 if the last pass removed nothing (or the set emptied)  */
+    double  mass;            /* sum m over the bound set        (halo_properties.py:16)  */
+    double  com[3];          /* centre of mass                  (halo_properties.py:26)  */
+    double  vb[3];           /* bulk velocity used by the last pass / of the bound set   */
+    int64_t pairs;           /* (target, source) pairs evaluated over all passes         */
+} halma_halo_result;
+
+typedef struct halma_run_stats {
+    double  total_ms;        /* CUDA-event time of the whole run on the plan's stream    */
+    double  potential_ms;    /* sum over potential-kernel launches (CUDA events)         */
+    int32_t potential_launches;
+    int32_t launches;        /* all kernel launches issued by the run                    */
+    int32_t passes;          /* loop passes executed (max over haloes)                   */
+    int32_t reserved;
+    int64_t pairs;           /* interactions evaluated, summed over haloes and passes    */
+} halma_run_stats;
+
+/* offsets: int64[n_halo+1], ext_offsets[g]: int64[n_halo+1] for g < n_groups (host). */
+int halma_plan_create(const halma_unbind_config *cfg, int64_t n_halo, const int64_t *offsets,
+                      const int64_t *const *ext_offsets, halma_plan **out);
+void halma_plan_destroy(halma_plan *plan);
+
+/* Host float64 arrays of length offsets[n_halo] (the reference keeps particle data in
+ * float64; the float32 cast of positions and masses for the potential is done on the
+ * device with round-to-nearest, like np.float32(...) at halo_gas.py:172-178). */
+int halma_plan_upload_members(halma_plan *plan, const double *x, const double *y, const double *z,
+                              const double *vx, const double *vy, const double *vz,
+                              const double *mass);
+int halma_plan_upload_group(halma_plan *plan, int group, const double *mass, const double *x,
+                            const double *y, const double *z);
+/* vb: double[3*n_halo]; required when vb_fixed = 1. */
+int halma_plan_set_vb(halma_plan *plan, const double *vb);
+
+/* Split mode only: join an NCCL communicator.  unique_id is the 128-byte ncclUniqueId
+ * made by rank 0 (halma_nccl_unique_id) and broadcast by the caller. */
+int halma_nccl_unique_id(void *unique_id_128);
+int halma_plan_join(halma_plan *plan, const void *unique_id_128);
+
+/* Runs the whole loop on the device from the uploaded (pristine) inputs; can be called
+ * repeatedly.  Blocks until done; stats may be null. */
+int halma_plan_run(halma_plan *plan, halma_run_stats *stats);
+
+/* Any output pointer may be null.  mask/be/energy/idx are indexed like the member input
+ * arrays: mask uint8[N]; be float32[N] (sum m/r at the last pass the particle took part
+ * in); energy float64[N]; idx int32[N]: for halo h, idx[offsets[h] .. offsets[h]+n_bound)
+ * holds the ascending local indices of the bound members; halos: [n_halo]. */
+int halma_plan_download(halma_plan *plan, uint8_t *mask, float *be, double *energy, int32_t *idx,
+                        halma_halo_result *halos);
+
+/* One-shot convenience for a single halo without externals bookkeeping on the caller's
+ * side: create + upload + run + download + destroy.  groups_* are arrays of n_groups host
+ * pointers / lengths. */
+int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n,
+                      const double *x, const double *y, const double *z,
+                      const double *vx, const double *vy, const double *vz, const double *mass,
+                      const int64_t *group_n, const double *const *group_mass,
+                      const double *const *group_x, const double *const *group_y,
+                      const double *const *group_z, const double *vb,
+                      uint8_t *mask, float *be, double *energy, int32_t *idx,
+                      halma_halo_result *result, halma_run_stats *stats);
+
+/* ------------------------------------------------------------------------------------ *
+ * Pipe-rate microbenchmark used for the roofline denominator: measures
+ * MUFU.RSQ, FFMA and packed FFMA2 issue rates per SM per clock, and the SM clock during
+ * the measurement.  out: double[8] = {rsq_per_clk_sm, ffma_per_clk_sm, ffma2_per_clk_sm,
+ * sm_clock_mhz, sm_count, 0, 0, 0}.
+ * ------------------------------------------------------------------------------------ */
+int halma_microbench(int device, double *out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALMA_UNBIND_H */

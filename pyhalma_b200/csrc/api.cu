@@ -1,0 +1,944 @@
+// C-ABI of libhalma_unbind.so (include/halma_unbind.h): error handling, device contexts,
+// the f2py-level potential call and the unbinding plan with its device-resident loop.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "loop_kernels.h"
+#include "potential.h"
+
+using namespace halma;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            char b__[512];                                                                             \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                     __LINE__);                                                                        \
+            return fail(HALMA_ERR_CUDA, b__);                                                          \
+        }                                                                                              \
+    } while (0)
+
+extern "C" const char *halma_last_error(void) { return g_err.c_str(); }
+extern "C" int halma_abi_version(void) { return HALMA_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------
+// device contexts
+// ---------------------------------------------------------------------------------------
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    int bps[2] = {0, 0};          // resident potential blocks per SM, by mode
+    cudaStream_t stream = nullptr;
+    // grow-only scratch of the host-pointer potential call
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::mutex mu;
+};
+
+static DeviceCtx g_ctx[64];
+static std::mutex g_ctx_mu;
+
+static int get_ctx(int device, DeviceCtx **out)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(HALMA_ERR_NO_DEVICE, std::string("no usable CUDA device: ") +
+                                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                             " (libhalma_unbind has no CPU fallback)");
+    }
+    if (device < 0 || device >= n || device >= 64) return fail(HALMA_ERR_NO_DEVICE, "device index out of range");
+    CU_TRY(cudaSetDevice(device));
+    DeviceCtx &c = g_ctx[device];
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    if (!c.ready) {
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(HALMA_ERR_NO_DEVICE, "device is not sm_100 or newer; this library is built for sm_100a only");
+        c.sm_count = prop.multiProcessorCount;
+        CU_TRY(potential_configure(HALMA_MODE_FAST, &c.bps[HALMA_MODE_FAST]));
+        CU_TRY(potential_configure(HALMA_MODE_EXACT, &c.bps[HALMA_MODE_EXACT]));
+        CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.ready = true;
+    }
+    *out = &c;
+    return HALMA_OK;
+}
+
+extern "C" int halma_device_count(int *count)
+{
+    if (!count) return fail(HALMA_ERR_INVALID, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(HALMA_ERR_NO_DEVICE, cudaGetErrorString(e));
+    }
+    *count = n;
+    return HALMA_OK;
+}
+
+extern "C" int halma_device_info(int device, char *name, int len, int *sm_count, int *clock_khz, int64_t *mem_bytes)
+{
+    DeviceCtx *c;
+    int rc = get_ctx(device, &c);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (name && len > 0) {
+        strncpy(name, prop.name, len - 1);
+        name[len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (clock_khz) CU_TRY(cudaDeviceGetAttribute(clock_khz, cudaDevAttrClockRate, device));
+    if (mem_bytes) *mem_bytes = static_cast<int64_t>(prop.totalGlobalMem);
+    return HALMA_OK;
+}
+
+extern "C" int halma_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return fail(HALMA_ERR_INVALID, "bad arguments");
+    CU_TRY(cudaMallocHost(ptr, static_cast<size_t>(bytes > 0 ? bytes : 1)));
+    return HALMA_OK;
+}
+
+extern "C" int halma_host_free(void *ptr)
+{
+    if (ptr) CU_TRY(cudaFreeHost(ptr));
+    return HALMA_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+static inline int64_t up4(int64_t n) { return (n + 3) & ~int64_t(3); }
+static inline size_t up256(size_t n) { return (n + 255) & ~size_t(255); }
+
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n)
+    {
+        o.p = nullptr;
+        o.n = 0;
+    }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        return cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DBuf() { release(); }
+};
+
+static int choose_split(int mode, int64_t n_tgt, int64_t n_src, int group, int target_items)
+{
+    if (mode != HALMA_MODE_FAST) return 1;
+    const int64_t groups = (n_tgt + group - 1) / group;
+    if (groups <= 0 || groups >= target_items) return 1;
+    const int64_t want = (target_items + groups - 1) / groups;
+    const int64_t cap = std::max<int64_t>(1, n_src / kMinSplitSources);
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(cap, kMaxSplit))));
+}
+
+// ---------------------------------------------------------------------------------------
+// brute_force_binding_energy on device pointers
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct PotWorkspaceHeader {      // mirrored at the start of the device workspace
+    LoopState st;
+    HaloDesc halo;
+    int32_t order;
+    int32_t nsplit;
+    int32_t item_base[2];
+};
+
+constexpr size_t kPotHeaderBytes = 1024;
+static_assert(sizeof(PotWorkspaceHeader) <= kPotHeaderBytes, "header too large");
+
+__global__ void k_fold_to_f32(const double *__restrict__ phi_part, int64_t stride, int S, int64_t n,
+                              float *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        double phi = phi_part[i];
+        for (int k = 1; k < S; ++k) phi += phi_part[k * stride + i];
+        out[i] = __double2float_rn(phi);
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t halma_potential_workspace_bytes(int64_t n_src, int64_t n_tgt)
+{
+    (void)n_src;
+    if (n_tgt < 0) return 0;
+    return static_cast<int64_t>(kPotHeaderBytes) + kMaxSplit * up4(n_tgt) * 8 + 256;
+}
+
+static int potential_dev(DeviceCtx *c, int mode, const float *sm, const float *sx, const float *sy, const float *sz,
+                         int64_t n_src, const float *tx, const float *ty, const float *tz, int64_t n_tgt,
+                         float *out_be, void *workspace, cudaStream_t stream)
+{
+    if (n_tgt == 0) return HALMA_OK;
+    if (n_src == 0) {
+        CU_TRY(cudaMemsetAsync(out_be, 0, n_tgt * sizeof(float), stream));
+        return HALMA_OK;
+    }
+    const int group = potential_group_size(mode);
+    const int grid = c->sm_count * c->bps[mode];
+    const int target_items = 8 * grid * (kPotentialBlock / 32);
+    const int S = choose_split(mode, n_tgt, n_src, group, target_items);
+    const int64_t groups = (n_tgt + group - 1) / group;
+
+    PotWorkspaceHeader hdr;
+    memset(&hdr, 0, sizeof hdr);
+    hdr.st.n_items = static_cast<int32_t>(groups * S);
+    hdr.st.any_active = 1;
+    hdr.halo.poff = 0;
+    hdr.halo.uoff = 0;
+    hdr.halo.n0 = static_cast<int32_t>(n_tgt);
+    hdr.halo.nseg = 1;
+    hdr.halo.n_ext = static_cast<int32_t>(n_src);
+    hdr.halo.seg[0].begin = 0;
+    hdr.halo.seg[0].count = static_cast<int32_t>(n_src);
+    hdr.halo.seg[0].flags = kSegNewClass;
+    hdr.order = 0;
+    hdr.nsplit = S;
+    hdr.item_base[0] = 0;
+    hdr.item_base[1] = hdr.st.n_items;
+    char *ws = static_cast<char *>(workspace);
+    CU_TRY(cudaMemcpyAsync(ws, &hdr, sizeof hdr, cudaMemcpyHostToDevice, stream));
+    PotWorkspaceHeader *d = reinterpret_cast<PotWorkspaceHeader *>(ws);
+
+    PotParams p;
+    memset(&p, 0, sizeof p);
+    p.tx[0] = p.tx[1] = tx;
+    p.ty[0] = p.ty[1] = ty;
+    p.tz[0] = p.tz[1] = tz;
+    p.src[2] = F32Set{sx, sy, sz, sm};
+    p.halo = &d->halo;
+    p.cnt = nullptr;
+    p.order = &d->order;
+    p.item_base = d->item_base;
+    p.nsplit = &d->nsplit;
+    p.st = &d->st;
+    p.phi_part = reinterpret_cast<double *>(ws + kPotHeaderBytes);
+    p.phi_stride = up4(n_tgt);
+    p.n_halo = 1;
+    p.tgt_members = 0;
+    p.rank = 0;
+    p.n_ranks = 1;
+    CU_TRY(potential_launch(p, mode, grid, stream));
+    const int fb = static_cast<int>(std::min<int64_t>((n_tgt + 255) / 256, c->sm_count * 8));
+    k_fold_to_f32<<<fb, 256, 0, stream>>>(p.phi_part, p.phi_stride, S, n_tgt, out_be);
+    CU_TRY(cudaGetLastError());
+    return HALMA_OK;
+}
+
+static int check_mode(int mode)
+{
+    if (mode != HALMA_MODE_FAST && mode != HALMA_MODE_EXACT) return fail(HALMA_ERR_INVALID, "unknown mode");
+    return HALMA_OK;
+}
+
+extern "C" int halma_potential_f32_dev(int device, int mode, const float *src_m, const float *src_x,
+                                       const float *src_y, const float *src_z, int64_t n_src, const float *tgt_x,
+                                       const float *tgt_y, const float *tgt_z, int64_t n_tgt, float *out_be,
+                                       void *workspace, void *stream)
+{
+    if (int rc = check_mode(mode)) return rc;
+    if (n_src < 0 || n_tgt < 0) return fail(HALMA_ERR_INVALID, "negative size");
+    if (n_src > 0x7ffffff0ll || n_tgt > 0x7ffffff0ll) return fail(HALMA_ERR_TOO_LARGE, "more than 2^31-16 particles");
+    if (n_tgt == 0) return HALMA_OK;
+    if (!out_be || !tgt_x || !tgt_y || !tgt_z || !workspace) return fail(HALMA_ERR_INVALID, "null pointer");
+    if (n_src > 0 && (!src_m || !src_x || !src_y || !src_z)) return fail(HALMA_ERR_INVALID, "null source pointer");
+    const void *al[] = {src_m, src_x, src_y, src_z, workspace};
+    for (const void *q : al)
+        if (reinterpret_cast<uintptr_t>(q) & 15) return fail(HALMA_ERR_ALIGN, "device pointer not 16-byte aligned");
+    DeviceCtx *c;
+    if (int rc = get_ctx(device, &c)) return rc;
+    return potential_dev(c, mode, src_m, src_x, src_y, src_z, n_src, tgt_x, tgt_y, tgt_z, n_tgt, out_be, workspace,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int halma_potential_f32(int device, int mode, const float *src_m, const float *src_x, const float *src_y,
+                                   const float *src_z, int64_t n_src, const float *tgt_x, const float *tgt_y,
+                                   const float *tgt_z, int64_t n_tgt, float *out_be)
+{
+    if (int rc = check_mode(mode)) return rc;
+    if (n_src < 0 || n_tgt < 0) return fail(HALMA_ERR_INVALID, "negative size");
+    if (n_src > 0x7ffffff0ll || n_tgt > 0x7ffffff0ll) return fail(HALMA_ERR_TOO_LARGE, "more than 2^31-16 particles");
+    if (n_tgt == 0) return HALMA_OK;
+    if (!out_be || !tgt_x || !tgt_y || !tgt_z) return fail(HALMA_ERR_INVALID, "null pointer");
+    if (n_src > 0 && (!src_m || !src_x || !src_y || !src_z)) return fail(HALMA_ERR_INVALID, "null source pointer");
+    DeviceCtx *c;
+    if (int rc = get_ctx(device, &c)) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    const size_t sb = up256((n_src + 4) * sizeof(float)), tb = up256((n_tgt + 4) * sizeof(float));
+    const size_t wb = up256(static_cast<size_t>(halma_potential_workspace_bytes(n_src, n_tgt)));
+    const size_t need = 4 * sb + 4 * tb + wb;
+    if (need > c->scratch_bytes) {
+        if (c->scratch) CU_TRY(cudaFree(c->scratch));
+        c->scratch = nullptr;
+        c->scratch_bytes = 0;
+        CU_TRY(cudaMalloc(&c->scratch, need + need / 4));
+        c->scratch_bytes = need + need / 4;
+    }
+    char *base = static_cast<char *>(c->scratch);
+    float *d_s[4], *d_t[4];
+    for (int k = 0; k < 4; ++k) d_s[k] = reinterpret_cast<float *>(base + k * sb);
+    for (int k = 0; k < 4; ++k) d_t[k] = reinterpret_cast<float *>(base + 4 * sb + k * tb);
+    void *d_ws = base + 4 * sb + 4 * tb;
+    cudaStream_t s = c->stream;
+    const float *hs[4] = {src_m, src_x, src_y, src_z};
+    for (int k = 0; k < 4 && n_src > 0; ++k)
+        CU_TRY(cudaMemcpyAsync(d_s[k], hs[k], n_src * sizeof(float), cudaMemcpyHostToDevice, s));
+    const float *ht[3] = {tgt_x, tgt_y, tgt_z};
+    for (int k = 0; k < 3; ++k) CU_TRY(cudaMemcpyAsync(d_t[k], ht[k], n_tgt * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = potential_dev(c, mode, d_s[0], d_s[1], d_s[2], d_s[3], n_src, d_t[0], d_t[1], d_t[2], n_tgt, d_t[3],
+                           d_ws, s);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(out_be, d_t[3], n_tgt * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return HALMA_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL, loaded lazily (split mode only)
+// ---------------------------------------------------------------------------------------
+struct UID128 {      // ncclUniqueId: 128 opaque bytes, passed by value
+    char internal[128];
+};
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, UID128, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static int load_nccl()
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.handle) return HALMA_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(HALMA_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(HALMA_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+    g_nccl.handle = h;
+    return HALMA_OK;
+}
+
+static int nccl_fail(int code, const char *what)
+{
+    return fail(HALMA_ERR_NCCL, std::string(what) + ": " +
+                                    (g_nccl.GetErrorString ? g_nccl.GetErrorString(code) : "nccl error"));
+}
+
+extern "C" int halma_nccl_unique_id(void *unique_id_128)
+{
+    if (!unique_id_128) return fail(HALMA_ERR_INVALID, "null pointer");
+    if (int rc = load_nccl()) return rc;
+    int e = g_nccl.GetUniqueId(unique_id_128);
+    return e ? nccl_fail(e, "ncclGetUniqueId") : HALMA_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+struct halma_plan {
+    halma_unbind_config cfg;
+    DeviceCtx *ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t n_halo = 0, n_user = 0, n_pad = 0, n_ext_pad = 0;
+    int n_chunks = 0;
+    std::vector<int64_t> offsets;
+    std::vector<std::vector<int64_t>> ext_offsets;
+    std::vector<int> group_seg;           // segment index of each ext group inside HaloDesc::seg
+    std::vector<int> group_max;           // largest per-halo count of each group
+    bool members_up = false, vb_up = false;
+    std::vector<bool> group_up;
+
+    // static tables
+    DBuf<HaloDesc> d_halo;
+    DBuf<int32_t> d_chunk_halo, d_chunk_p0, d_order;
+    std::vector<DBuf<int64_t>> d_ext_off;
+    // inputs
+    DBuf<double> d_in;                    // 7 * n_user: x y z vx vy vz m
+    DBuf<float> d_ext;                    // 4 * n_ext_pad: x y z m
+    DBuf<double> d_stage;                 // staging for one ext group upload (4 * max group size)
+    DBuf<double> d_vb_user;
+    // working sets
+    DBuf<float> d_work;                   // 2 * 4 * n_pad
+    DBuf<int32_t> d_widx;                 // 2 * n_pad
+    DBuf<int32_t> d_hint;                 // per-halo int arrays: 9 * n_halo + (n_halo + 1)
+    DBuf<double> d_hdbl;                  // per-halo doubles: M(1) vb(3) vb_next(3) com(3)
+    DBuf<unsigned long long> d_pairs;
+    DBuf<int32_t> d_cint;                 // per-chunk ints: cnt, off
+    DBuf<double> d_csum;                  // 7 per chunk
+    DBuf<uint8_t> d_flag, d_mask;
+    DBuf<float> d_be;
+    DBuf<double> d_E;
+    DBuf<int32_t> d_idx;
+    DBuf<double> d_phi;
+    DBuf<LoopState> d_st;
+    int32_t *h_flags = nullptr;           // pinned: any_active after each pass
+    std::vector<cudaEvent_t> ev;          // per pass: before K1, after K1, end of pass
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    void *comm = nullptr;                 // ncclComm_t (split mode)
+    bool ran = false;
+    LoopParams lp;
+    PotParams pp;
+
+    ~halma_plan()
+    {
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        for (auto e : ev) cudaEventDestroy(e);
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_stop) cudaEventDestroy(ev_stop);
+        if (h_flags) cudaFreeHost(h_flags);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *const *ext_offsets)
+{
+    const halma_unbind_config &cfg = P->cfg;
+    const int64_t nh = P->n_halo;
+    P->offsets.assign(offsets, offsets + nh + 1);
+    if (P->offsets[0] != 0) return fail(HALMA_ERR_INVALID, "offsets[0] must be 0");
+    for (int64_t h = 0; h < nh; ++h)
+        if (P->offsets[h + 1] < P->offsets[h]) return fail(HALMA_ERR_INVALID, "offsets must be non-decreasing");
+    P->n_user = P->offsets[nh];
+    if (P->n_user > 0x7ffffff0ll) return fail(HALMA_ERR_TOO_LARGE, "more than 2^31-16 members");
+    P->ext_offsets.resize(cfg.n_groups);
+    P->group_up.assign(cfg.n_groups, false);
+    P->group_max.assign(cfg.n_groups, 0);
+    for (int g = 0; g < cfg.n_groups; ++g) {
+        if (!ext_offsets || !ext_offsets[g]) return fail(HALMA_ERR_INVALID, "ext_offsets missing for a group");
+        P->ext_offsets[g].assign(ext_offsets[g], ext_offsets[g] + nh + 1);
+        if (P->ext_offsets[g][0] != 0) return fail(HALMA_ERR_INVALID, "ext_offsets[g][0] must be 0");
+        for (int64_t h = 0; h < nh; ++h) {
+            const int64_t c = P->ext_offsets[g][h + 1] - P->ext_offsets[g][h];
+            if (c < 0) return fail(HALMA_ERR_INVALID, "ext_offsets must be non-decreasing");
+            if (c > 0x7ffffff0ll) return fail(HALMA_ERR_TOO_LARGE, "external group too large");
+            P->group_max[g] = std::max<int>(P->group_max[g], static_cast<int>(c));
+        }
+    }
+
+    // segment order (see include/halma_unbind.h): which HaloDesc::seg slot each group lands in
+    P->group_seg.assign(cfg.n_groups, 0);
+    int members_slot;
+    if (cfg.split_classes) {
+        members_slot = 0;
+        for (int g = 0; g < cfg.n_groups; ++g) P->group_seg[g] = 1 + g;
+    } else {
+        members_slot = cfg.n_pre;
+        for (int g = 0; g < cfg.n_groups; ++g) P->group_seg[g] = g < cfg.n_pre ? g : g + 1;
+    }
+
+    std::vector<HaloDesc> halo(nh);
+    std::vector<int32_t> chunk_halo, chunk_p0;
+    int64_t poff = 0, eoff = 0;
+    for (int64_t h = 0; h < nh; ++h) {
+        HaloDesc &d = halo[h];
+        memset(&d, 0, sizeof d);
+        const int64_t n0 = P->offsets[h + 1] - P->offsets[h];
+        d.poff = poff;
+        d.uoff = P->offsets[h];
+        d.n0 = static_cast<int32_t>(n0);
+        d.nseg = 1 + cfg.n_groups;
+        d.chunk_begin = static_cast<int32_t>(chunk_halo.size());
+        for (int64_t q = 0; q < n0; q += kChunk) {
+            chunk_halo.push_back(static_cast<int32_t>(h));
+            chunk_p0.push_back(static_cast<int32_t>(q));
+        }
+        d.seg[members_slot].begin = poff;
+        d.seg[members_slot].count = d.n0;
+        d.seg[members_slot].flags = kSegMembers | (cfg.split_classes ? kSegNewClass : 0);
+        int64_t next = 0;
+        for (int g = 0; g < cfg.n_groups; ++g) {
+            const int64_t c = P->ext_offsets[g][h + 1] - P->ext_offsets[g][h];
+            SegDesc &s = d.seg[P->group_seg[g]];
+            s.begin = eoff;
+            s.count = static_cast<int32_t>(c);
+            s.flags = cfg.split_classes ? kSegNewClass : 0;
+            eoff += up4(c);
+            next += c;
+        }
+        if (next > 0x7ffffff0ll) return fail(HALMA_ERR_TOO_LARGE, "too many external sources for one halo");
+        d.n_ext = static_cast<int32_t>(next);
+        poff += up4(n0);
+    }
+    P->n_pad = poff + 16;
+    P->n_ext_pad = eoff + 16;
+    P->n_chunks = static_cast<int>(chunk_halo.size());
+
+    std::vector<int32_t> order(nh);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return halo[a].n0 > halo[b].n0; });
+
+    cudaStream_t s = P->stream;
+    CU_TRY(P->d_halo.alloc(nh));
+    CU_TRY(P->d_chunk_halo.alloc(chunk_halo.size()));
+    CU_TRY(P->d_chunk_p0.alloc(chunk_p0.size()));
+    CU_TRY(P->d_order.alloc(nh));
+    if (nh) {
+        CU_TRY(cudaMemcpyAsync(P->d_halo.p, halo.data(), nh * sizeof(HaloDesc), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(P->d_order.p, order.data(), nh * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    }
+    if (P->n_chunks) {
+        CU_TRY(cudaMemcpyAsync(P->d_chunk_halo.p, chunk_halo.data(), chunk_halo.size() * 4, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(P->d_chunk_p0.p, chunk_p0.data(), chunk_p0.size() * 4, cudaMemcpyHostToDevice, s));
+    }
+    P->d_ext_off.resize(cfg.n_groups);
+    int64_t stage = 0;
+    for (int g = 0; g < cfg.n_groups; ++g) {
+        CU_TRY(P->d_ext_off[g].alloc(nh + 1));
+        CU_TRY(cudaMemcpyAsync(P->d_ext_off[g].p, P->ext_offsets[g].data(), (nh + 1) * 8, cudaMemcpyHostToDevice, s));
+        stage = std::max<int64_t>(stage, P->ext_offsets[g][nh]);
+    }
+    CU_TRY(cudaStreamSynchronize(s));      // host vectors go out of scope
+
+    const size_t NU = static_cast<size_t>(P->n_user), NP = static_cast<size_t>(P->n_pad);
+    CU_TRY(P->d_in.alloc(7 * NU));
+    CU_TRY(P->d_ext.alloc(4 * static_cast<size_t>(P->n_ext_pad)));
+    CU_TRY(P->d_stage.alloc(4 * static_cast<size_t>(stage)));
+    CU_TRY(P->d_vb_user.alloc(3 * nh));
+    CU_TRY(P->d_work.alloc(8 * NP));
+    CU_TRY(P->d_widx.alloc(2 * NP));
+    CU_TRY(P->d_hint.alloc(9 * nh + nh + 1));
+    CU_TRY(P->d_hdbl.alloc(10 * nh));
+    CU_TRY(P->d_pairs.alloc(nh));
+    CU_TRY(P->d_cint.alloc(2 * static_cast<size_t>(P->n_chunks)));
+    CU_TRY(P->d_csum.alloc(7 * static_cast<size_t>(P->n_chunks)));
+    CU_TRY(P->d_flag.alloc(NP));
+    CU_TRY(P->d_mask.alloc(NU));
+    CU_TRY(P->d_be.alloc(NU));
+    CU_TRY(P->d_E.alloc(NU));
+    CU_TRY(P->d_idx.alloc(NU));
+    const int planes = cfg.mode == HALMA_MODE_FAST ? kMaxSplit : 1;
+    CU_TRY(P->d_phi.alloc(planes * NP));
+    CU_TRY(P->d_st.alloc(1));
+    CU_TRY(cudaMemsetAsync(P->d_work.p, 0, 8 * NP * sizeof(float), s));
+    CU_TRY(cudaMemsetAsync(P->d_ext.p, 0, 4 * static_cast<size_t>(P->n_ext_pad) * sizeof(float), s));
+    CU_TRY(cudaMemsetAsync(P->d_vb_user.p, 0, 3 * nh * sizeof(double), s));
+    CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&P->h_flags), sizeof(int32_t) * (cfg.max_iter + 1)));
+    P->ev.resize(3 * static_cast<size_t>(cfg.max_iter));
+    for (auto &e : P->ev) CU_TRY(cudaEventCreate(&e));
+    CU_TRY(cudaEventCreate(&P->ev_start));
+    CU_TRY(cudaEventCreate(&P->ev_stop));
+
+    // parameter blocks
+    LoopParams &L = P->lp;
+    memset(&L, 0, sizeof L);
+    L.halo = P->d_halo.p;
+    L.chunk_halo = P->d_chunk_halo.p;
+    L.chunk_p0 = P->d_chunk_p0.p;
+    L.order = P->d_order.p;
+    L.n_halo = static_cast<int32_t>(nh);
+    L.n_chunks = P->n_chunks;
+    L.n_pad = P->n_pad;
+    L.n_user = P->n_user;
+    const double *in = P->d_in.p;
+    L.x64 = in;
+    L.y64 = in + NU;
+    L.z64 = in + 2 * NU;
+    L.vx = in + 3 * NU;
+    L.vy = in + 4 * NU;
+    L.vz = in + 5 * NU;
+    L.m64 = in + 6 * NU;
+    for (int b = 0; b < 2; ++b) {
+        float *w = P->d_work.p + b * 4 * NP;
+        L.wx[b] = w;
+        L.wy[b] = w + NP;
+        L.wz[b] = w + 2 * NP;
+        L.wm[b] = w + 3 * NP;
+        L.widx[b] = P->d_widx.p + b * NP;
+    }
+    int32_t *hi = P->d_hint.p;
+    L.cnt = hi;
+    L.cnt_next = hi + nh;
+    L.iter = hi + 2 * nh;
+    L.active = hi + 3 * nh;
+    L.active_next = hi + 4 * nh;
+    L.halo_buf = hi + 5 * nh;
+    L.nsplit = hi + 6 * nh;
+    L.converged = hi + 7 * nh;
+    L.item_base = hi + 9 * nh;       // n_halo + 1 entries (slot 8 is spare)
+    double *hd = P->d_hdbl.p;
+    L.hM = hd;
+    L.hvb = hd + nh;
+    L.hvb_next = hd + 4 * nh;
+    L.hcom = hd + 7 * nh;
+    L.pairs = P->d_pairs.p;
+    L.chunk_cnt = P->d_cint.p;
+    L.chunk_off = P->d_cint.p + P->n_chunks;
+    L.chunk_sum = P->d_csum.p;
+    L.flag = P->d_flag.p;
+    L.out_mask = P->d_mask.p;
+    L.out_be = P->d_be.p;
+    L.out_E = P->d_E.p;
+    L.out_idx = P->d_idx.p;
+    L.phi_part = P->d_phi.p;
+    L.st = P->d_st.p;
+    L.G32 = static_cast<float>(cfg.G);           // numpy: float32 array *= python float
+    L.kappa32 = static_cast<float>(cfg.kappa);
+    L.vb_fixed = cfg.vb_fixed;
+    L.max_iter = cfg.max_iter;
+    L.mode = cfg.mode;
+    L.group_size = potential_group_size(cfg.mode);
+    L.rank = cfg.rank;
+    L.n_ranks = cfg.n_ranks;
+    const int grid = P->ctx->sm_count * P->ctx->bps[cfg.mode];
+    L.target_items = 8 * grid * (kPotentialBlock / 32);
+    L.max_split = planes;
+
+    PotParams &Q = P->pp;
+    memset(&Q, 0, sizeof Q);
+    for (int b = 0; b < 2; ++b) {
+        Q.tx[b] = L.wx[b];
+        Q.ty[b] = L.wy[b];
+        Q.tz[b] = L.wz[b];
+        Q.src[b] = F32Set{L.wx[b], L.wy[b], L.wz[b], L.wm[b]};
+    }
+    const size_t NE = static_cast<size_t>(P->n_ext_pad);
+    Q.src[2] = F32Set{P->d_ext.p, P->d_ext.p + NE, P->d_ext.p + 2 * NE, P->d_ext.p + 3 * NE};
+    Q.halo = L.halo;
+    Q.cnt = L.cnt;
+    Q.order = L.order;
+    Q.item_base = L.item_base;
+    Q.nsplit = L.nsplit;
+    Q.st = L.st;
+    Q.phi_part = L.phi_part;
+    Q.phi_stride = P->n_pad;
+    Q.n_halo = L.n_halo;
+    Q.tgt_members = 1;
+    Q.rank = cfg.rank;
+    Q.n_ranks = cfg.n_ranks;
+    CU_TRY(cudaStreamSynchronize(s));
+    return HALMA_OK;
+}
+
+extern "C" int halma_plan_create(const halma_unbind_config *cfg, int64_t n_halo, const int64_t *offsets,
+                                 const int64_t *const *ext_offsets, halma_plan **out)
+{
+    if (!cfg || !offsets || !out) return fail(HALMA_ERR_INVALID, "null pointer");
+    if (cfg->struct_size != static_cast<int32_t>(sizeof(halma_unbind_config)))
+        return fail(HALMA_ERR_INVALID, "halma_unbind_config size mismatch (ABI)");
+    if (int rc = check_mode(cfg->mode)) return rc;
+    if (n_halo < 0 || n_halo > 0x7ffffff0ll) return fail(HALMA_ERR_INVALID, "bad n_halo");
+    if (cfg->n_groups < 0 || cfg->n_groups > HALMA_MAX_GROUPS) return fail(HALMA_ERR_INVALID, "bad n_groups");
+    if (cfg->n_pre < 0 || cfg->n_pre > cfg->n_groups) return fail(HALMA_ERR_INVALID, "bad n_pre");
+    if (cfg->split_classes && cfg->n_pre != 0) return fail(HALMA_ERR_INVALID, "split_classes requires n_pre = 0");
+    if (cfg->max_iter < 1 || cfg->max_iter > 4096) return fail(HALMA_ERR_INVALID, "max_iter must be in 1..4096");
+    if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) return fail(HALMA_ERR_INVALID, "bad rank");
+    if (cfg->n_ranks > 1 && n_halo != 1) return fail(HALMA_ERR_INVALID, "split mode shares exactly one halo");
+    DeviceCtx *c;
+    if (int rc = get_ctx(cfg->device, &c)) return rc;
+    halma_plan *P = new halma_plan();
+    P->cfg = *cfg;
+    P->ctx = c;
+    P->n_halo = n_halo;
+    cudaError_t e = cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete P;
+        return fail(HALMA_ERR_CUDA, cudaGetErrorString(e));
+    }
+    int rc = plan_build(P, offsets, ext_offsets);
+    if (rc) {
+        delete P;
+        return rc;
+    }
+    *out = P;
+    return HALMA_OK;
+}
+
+extern "C" void halma_plan_destroy(halma_plan *plan)
+{
+    if (!plan) return;
+    cudaSetDevice(plan->cfg.device);
+    cudaStreamSynchronize(plan->stream);
+    delete plan;
+}
+
+extern "C" int halma_plan_upload_members(halma_plan *P, const double *x, const double *y, const double *z,
+                                         const double *vx, const double *vy, const double *vz, const double *mass)
+{
+    if (!P) return fail(HALMA_ERR_INVALID, "null plan");
+    const double *src[7] = {x, y, z, vx, vy, vz, mass};
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    const size_t NU = static_cast<size_t>(P->n_user);
+    for (int k = 0; k < 7; ++k) {
+        if (NU && !src[k]) return fail(HALMA_ERR_INVALID, "null member array");
+        if (NU) CU_TRY(cudaMemcpyAsync(P->d_in.p + k * NU, src[k], NU * 8, cudaMemcpyHostToDevice, P->stream));
+    }
+    P->members_up = true;
+    return HALMA_OK;
+}
+
+extern "C" int halma_plan_upload_group(halma_plan *P, int group, const double *mass, const double *x, const double *y,
+                                       const double *z)
+{
+    if (!P) return fail(HALMA_ERR_INVALID, "null plan");
+    if (group < 0 || group >= P->cfg.n_groups) return fail(HALMA_ERR_INVALID, "bad group index");
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    const size_t n = static_cast<size_t>(P->ext_offsets[group][P->n_halo]);
+    if (n) {
+        if (!mass || !x || !y || !z) return fail(HALMA_ERR_INVALID, "null group array");
+        const double *src[4] = {mass, x, y, z};
+        // the staging buffer is reused by the next group: stream order keeps this safe
+        for (int k = 0; k < 4; ++k)
+            CU_TRY(cudaMemcpyAsync(P->d_stage.p + k * n, src[k], n * 8, cudaMemcpyHostToDevice, P->stream));
+        const size_t NE = static_cast<size_t>(P->n_ext_pad);
+        float *e = P->d_ext.p;
+        CU_TRY(launch_pack_group(P->d_halo.p, static_cast<int>(P->n_halo), P->group_seg[group], P->group_max[group],
+                                 P->d_ext_off[group].p, P->d_stage.p, P->d_stage.p + n, P->d_stage.p + 2 * n,
+                                 P->d_stage.p + 3 * n, e + 3 * NE, e, e + NE, e + 2 * NE, P->stream));
+    }
+    P->group_up[group] = true;
+    return HALMA_OK;
+}
+
+extern "C" int halma_plan_set_vb(halma_plan *P, const double *vb)
+{
+    if (!P || !vb) return fail(HALMA_ERR_INVALID, "null pointer");
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    if (P->n_halo)
+        CU_TRY(cudaMemcpyAsync(P->d_vb_user.p, vb, 3 * P->n_halo * 8, cudaMemcpyHostToDevice, P->stream));
+    P->vb_up = true;
+    return HALMA_OK;
+}
+
+extern "C" int halma_plan_join(halma_plan *P, const void *unique_id_128)
+{
+    if (!P || !unique_id_128) return fail(HALMA_ERR_INVALID, "null pointer");
+    if (P->cfg.n_ranks < 2) return fail(HALMA_ERR_STATE, "plan was not created in split mode");
+    if (int rc = load_nccl()) return rc;
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    UID128 id;
+    memcpy(&id, unique_id_128, sizeof id);
+    int e = g_nccl.CommInitRank(&P->comm, P->cfg.n_ranks, id, P->cfg.rank);
+    return e ? nccl_fail(e, "ncclCommInitRank") : HALMA_OK;
+}
+
+static int enqueue_pass(halma_plan *P, int pass)
+{
+    cudaStream_t s = P->stream;
+    const int sm = P->ctx->sm_count;
+    const int grid = sm * P->ctx->bps[P->cfg.mode];
+    CU_TRY(cudaEventRecord(P->ev[3 * pass], s));
+    CU_TRY(potential_launch(P->pp, P->cfg.mode, grid, s));
+    CU_TRY(cudaEventRecord(P->ev[3 * pass + 1], s));
+    if (P->cfg.n_ranks > 1) {
+        CU_TRY(launch_fold_partials(P->lp, sm, s));
+        int e = g_nccl.AllReduce(P->d_phi.p, P->d_phi.p, static_cast<size_t>(P->n_pad), /*ncclFloat64*/ 8,
+                                 /*ncclSum*/ 0, P->comm, s);
+        if (e) return nccl_fail(e, "ncclAllReduce");
+        CU_TRY(launch_set_nsplit_one(P->lp, s));
+    }
+    CU_TRY(launch_energy_flag(P->lp, sm, s));
+    CU_TRY(launch_halo_decide(P->lp, 0, sm, s));
+    CU_TRY(launch_compact(P->lp, sm, s));
+    CU_TRY(launch_schedule(P->lp, 0, s));
+    CU_TRY(cudaMemcpyAsync(&P->h_flags[pass], &P->d_st.p->any_active, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaEventRecord(P->ev[3 * pass + 2], s));
+    return HALMA_OK;
+}
+
+extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
+{
+    if (!P) return fail(HALMA_ERR_INVALID, "null plan");
+    if (!P->members_up) return fail(HALMA_ERR_STATE, "members were not uploaded");
+    for (int g = 0; g < P->cfg.n_groups; ++g)
+        if (!P->group_up[g]) return fail(HALMA_ERR_STATE, "an external group was not uploaded");
+    if (P->cfg.vb_fixed && !P->vb_up) return fail(HALMA_ERR_STATE, "vb_fixed = 1 but halma_plan_set_vb was not called");
+    if (P->cfg.n_ranks > 1 && !P->comm) return fail(HALMA_ERR_STATE, "split mode needs halma_plan_join first");
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    cudaStream_t s = P->stream;
+    const int sm = P->ctx->sm_count;
+    const size_t NU = static_cast<size_t>(P->n_user);
+    const int nh = static_cast<int>(P->n_halo);
+    int launches = 0, pot_launches = 0, passes = 0;
+
+    CU_TRY(cudaEventRecord(P->ev_start, s));
+    CU_TRY(cudaMemsetAsync(P->d_st.p, 0, sizeof(LoopState), s));
+    CU_TRY(cudaMemsetAsync(P->d_mask.p, 0, NU, s));
+    CU_TRY(cudaMemsetAsync(P->d_be.p, 0, NU * sizeof(float), s));
+    CU_TRY(cudaMemsetAsync(P->d_E.p, 0, NU * sizeof(double), s));
+    CU_TRY(cudaMemsetAsync(P->d_hint.p, 0, P->d_hint.n * sizeof(int32_t), s));
+    if (P->cfg.vb_fixed && nh)
+        CU_TRY(cudaMemcpyAsync(P->lp.hvb, P->d_vb_user.p, 3 * nh * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (nh > 0) {
+        CU_TRY(launch_pack_members(P->lp, sm, s));
+        CU_TRY(launch_halo_decide(P->lp, 1, sm, s));
+        CU_TRY(launch_schedule(P->lp, 1, s));
+        launches += 3;
+        // Enqueue passes ahead of the device; a pinned flag written at the end of each pass
+        // tells the host when the loop has converged.  The device never waits for the host:
+        // pass k+kAhead is queued before the host looks at the flag of pass k, and a pass
+        // queued after convergence returns at once (any_active == 0).
+        constexpr int kAhead = 2;
+        const int max_iter = P->cfg.max_iter;
+        int queued = 0;
+        bool done = false;
+        while (!done) {
+            while (queued < max_iter && queued < passes + kAhead) {
+                if (int rc = enqueue_pass(P, queued)) return rc;
+                ++queued;
+            }
+            if (passes >= queued) break;
+            CU_TRY(cudaEventSynchronize(P->ev[3 * passes + 2]));
+            const int still = P->h_flags[passes];
+            ++passes;
+            if (!still) done = true;
+        }
+        launches += queued * (5 + (P->cfg.n_ranks > 1 ? 2 : 0));
+        pot_launches = queued;
+        CU_TRY(launch_finalize(P->lp, sm, s));
+        ++launches;
+    }
+    CU_TRY(cudaEventRecord(P->ev_stop, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    P->ran = true;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, P->ev_start, P->ev_stop));
+        stats->total_ms = ms;
+        double pot = 0.0;
+        for (int k = 0; k < pot_launches; ++k) {
+            CU_TRY(cudaEventElapsedTime(&ms, P->ev[3 * k], P->ev[3 * k + 1]));
+            pot += ms;
+        }
+        stats->potential_ms = pot;
+        stats->potential_launches = pot_launches;
+        stats->launches = launches;
+        stats->passes = passes;
+        if (nh) {
+            std::vector<unsigned long long> pr(nh);
+            CU_TRY(cudaMemcpy(pr.data(), P->d_pairs.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            unsigned long long t = 0;
+            for (auto v : pr) t += v;
+            stats->pairs = static_cast<int64_t>(t);
+        }
+    }
+    return HALMA_OK;
+}
+
+extern "C" int halma_plan_download(halma_plan *P, uint8_t *mask, float *be, double *energy, int32_t *idx,
+                                   halma_halo_result *halos)
+{
+    if (!P) return fail(HALMA_ERR_INVALID, "null plan");
+    if (!P->ran) return fail(HALMA_ERR_STATE, "halma_plan_run has not been called");
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    cudaStream_t s = P->stream;
+    const size_t NU = static_cast<size_t>(P->n_user);
+    const size_t nh = static_cast<size_t>(P->n_halo);
+    if (NU) {
+        if (mask) CU_TRY(cudaMemcpyAsync(mask, P->d_mask.p, NU, cudaMemcpyDeviceToHost, s));
+        if (be) CU_TRY(cudaMemcpyAsync(be, P->d_be.p, NU * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (energy) CU_TRY(cudaMemcpyAsync(energy, P->d_E.p, NU * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (idx) CU_TRY(cudaMemcpyAsync(idx, P->d_idx.p, NU * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (halos && nh) {
+        std::vector<int32_t> hi(P->d_hint.n);
+        std::vector<double> hd(P->d_hdbl.n);
+        std::vector<unsigned long long> pr(nh);
+        CU_TRY(cudaMemcpyAsync(hi.data(), P->d_hint.p, hi.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(hd.data(), P->d_hdbl.p, hd.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(pr.data(), P->d_pairs.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        for (size_t h = 0; h < nh; ++h) {
+            halma_halo_result &r = halos[h];
+            r.n_bound = hi[h];
+            r.n_iter = hi[2 * nh + h];
+            r.converged = hi[7 * nh + h];
+            r.mass = hd[h];
+            for (int k = 0; k < 3; ++k) {
+                r.vb[k] = hd[nh + 3 * h + k];
+                r.com[k] = hd[7 * nh + 3 * h + k];
+            }
+            r.pairs = static_cast<int64_t>(pr[h]);
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    return HALMA_OK;
+}
+
+extern "C" int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n, const double *x, const double *y,
+                                 const double *z, const double *vx, const double *vy, const double *vz,
+                                 const double *mass, const int64_t *group_n, const double *const *group_mass,
+                                 const double *const *group_x, const double *const *group_y,
+                                 const double *const *group_z, const double *vb, uint8_t *mask, float *be,
+                                 double *energy, int32_t *idx, halma_halo_result *result, halma_run_stats *stats)
+{
+    if (!cfg) return fail(HALMA_ERR_INVALID, "null config");
+    if (n < 0) return fail(HALMA_ERR_INVALID, "negative size");
+    if (cfg->n_groups > 0 && (!group_n || !group_mass || !group_x || !group_y || !group_z))
+        return fail(HALMA_ERR_INVALID, "null group table");
+    const int64_t offsets[2] = {0, n};
+    int64_t eo[HALMA_MAX_GROUPS][2];
+    const int64_t *eop[HALMA_MAX_GROUPS];
+    for (int g = 0; g < cfg->n_groups && g < HALMA_MAX_GROUPS; ++g) {
+        eo[g][0] = 0;
+        eo[g][1] = group_n[g];
+        eop[g] = eo[g];
+    }
+    halma_plan *P = nullptr;
+    int rc = halma_plan_create(cfg, 1, offsets, eop, &P);
+    if (rc) return rc;
+    rc = halma_plan_upload_members(P, x, y, z, vx, vy, vz, mass);
+    for (int g = 0; !rc && g < cfg->n_groups; ++g)
+        rc = halma_plan_upload_group(P, g, group_mass[g], group_x[g], group_y[g], group_z[g]);
+    if (!rc && cfg->vb_fixed) rc = vb ? halma_plan_set_vb(P, vb) : fail(HALMA_ERR_INVALID, "vb_fixed = 1 needs vb");
+    if (!rc) rc = halma_plan_run(P, stats);
+    if (!rc) rc = halma_plan_download(P, mask, be, energy, idx, result);
+    halma_plan_destroy(P);
+    return rc;
+}

@@ -1,0 +1,533 @@
+// Kernels 2 and 3 of the unbinding path and the device-side scheduler, sm_100a.
+//
+// One pass of the loop is five launches on one stream, none of which
+// needs the host:
+//   k_potential_*   (potential.cu)  Phi for every current member of every active halo
+//   k_energy_flag   energy step + bound flag + per-chunk survivor count and mass sums
+//                   (halo_properties.py:342-359 / halo_gas.py:456-476; sums :16-60)
+//   k_halo_decide   per halo: scan of chunk counts, reduction of chunk sums -> new count,
+//                   M, CoM, bulk velocity, converged / active
+//   k_compact       stable (order-preserving) warp-aggregated stream compaction of the
+//                   float32 working set into the other buffer
+//   k_schedule      commits the per-halo state, builds the ticket table of the next pass
+// All are O(N) and HBM-bound; the potential kernel dominates for N >~ 1e3.
+//
+// Reductions are done in a fixed order (tree inside a block, then ascending chunks), so a
+// run is bit-reproducible.
+#include "halma_common.cuh"
+#include "loop_kernels.h"
+
+namespace halma {
+
+namespace {
+
+constexpr int kCh = kChunk;      // 256 members per chunk == threads per block
+
+// Deterministic block-wide sum of NV doubles per thread (blockDim.x == kCh).
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* [NV * 8] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) smem[k * (kCh / 32) + warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (int w = 0; w < kCh / 32; ++w) s += smem[k * (kCh / 32) + w];
+            v[k] = s;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem /* [kCh/32 + 1] */, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kCh / 32 ? smem[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        if (lane < kCh / 32) smem[lane] = wi - w;
+        if (lane == kCh / 32 - 1) smem[kCh / 32] = wi;
+    }
+    __syncthreads();
+    const int r = smem[warp] + incl - v;
+    total = smem[kCh / 32];
+    __syncthreads();
+    return r;
+}
+
+// Groups of `gs` targets of a halo with n members that belong to this rank (split mode).
+__device__ __forceinline__ int my_groups(int n, int gs, int rank, int n_ranks)
+{
+    const int groups = (n + gs - 1) / gs;
+    return (groups - rank + n_ranks - 1) / n_ranks;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// Pack: float64 user arrays -> float32 working set (round to nearest, like np.float32()).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCh) k_pack_members(const LoopParams p)
+{
+    __shared__ double red[7 * (kCh / 32)];
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+        const int h = p.chunk_halo[c];
+        const HaloDesc &hd = p.halo[h];
+        const int q = p.chunk_p0[c] + threadIdx.x;
+        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        if (q < hd.n0) {
+            const int64_t i = hd.poff + q, g = hd.uoff + q;
+            const double x = p.x64[g], y = p.y64[g], z = p.z64[g], m = p.m64[g];
+            p.wx[0][i] = __double2float_rn(x);
+            p.wy[0][i] = __double2float_rn(y);
+            p.wz[0][i] = __double2float_rn(z);
+            p.wm[0][i] = __double2float_rn(m);
+            p.widx[0][i] = static_cast<int32_t>(g);
+            s[0] = m;
+            s[1] = m * p.vx[g];
+            s[2] = m * p.vy[g];
+            s[3] = m * p.vz[g];
+            s[4] = m * x;
+            s[5] = m * y;
+            s[6] = m * z;
+        }
+        block_sum<7>(s, red);
+        if (threadIdx.x == 0) {
+            p.chunk_cnt[c] = min(kCh, max(hd.n0 - p.chunk_p0[c], 0));
+#pragma unroll
+            for (int k = 0; k < 7; ++k) p.chunk_sum[static_cast<int64_t>(c) * 7 + k] = s[k];
+        }
+    }
+}
+
+// One external group: user CSR layout (float64) -> padded float32 segment of each halo.
+__global__ void __launch_bounds__(256) k_pack_group(const HaloDesc *halo, int n_halo, int seg_index,
+                                                    const int64_t *ext_off, const double *m, const double *x,
+                                                    const double *y, const double *z, float *em, float *ex,
+                                                    float *ey, float *ez)
+{
+    for (int h = blockIdx.y; h < n_halo; h += gridDim.y) {
+        const SegDesc sd = halo[h].seg[seg_index];
+        const int64_t u0 = ext_off[h];
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < sd.count; k += gridDim.x * blockDim.x) {
+            em[sd.begin + k] = __double2float_rn(m[u0 + k]);
+            ex[sd.begin + k] = __double2float_rn(x[u0 + k]);
+            ey[sd.begin + k] = __double2float_rn(y[u0 + k]);
+            ez[sd.begin + k] = __double2float_rn(z[u0 + k]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 2: energy step, bound flag, survivor counts and mass sums per chunk.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
+{
+    __shared__ double red[7 * (kCh / 32)];
+    if (!p.st->any_active) return;
+    const int par = p.st->parity;
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+        const int h = p.chunk_halo[c];
+        if (!p.active[h]) continue;
+        const int n = p.cnt[h];
+        const int p0 = p.chunk_p0[c];
+        if (p0 >= n) continue;
+        const HaloDesc &hd = p.halo[h];
+        const int q = p0 + threadIdx.x;
+        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        int bound = 0;
+        if (q < n) {
+            const int64_t i = hd.poff + q;
+            const int64_t g = p.widx[par][i];
+            // Phi: ascending sum of the j-split partials, rounded once to the f2py output dtype
+            const int S = p.nsplit[h];
+            double phi = p.phi_part[i];
+            for (int k = 1; k < S; ++k) phi += p.phi_part[static_cast<int64_t>(k) * p.n_pad + i];
+            const float be = __double2float_rn(phi);
+            // halo_properties.py:342-351 / halo_gas.py:456-465: float32 chain, two roundings
+            float pe = -be;
+            pe = __fmul_rn(pe, p.G32);
+            pe = __fmul_rn(pe, p.kappa32);
+            // :354 / :468  float64, no contraction: 0.5*((dvx^2 + dvy^2) + dvz^2)
+            const double dvx = __dsub_rn(p.vx[g], p.hvb[3 * h + 0]);
+            const double dvy = __dsub_rn(p.vy[g], p.hvb[3 * h + 1]);
+            const double dvz = __dsub_rn(p.vz[g], p.hvb[3 * h + 2]);
+            const double ke = __dmul_rn(
+                0.5, __dadd_rn(__dadd_rn(__dmul_rn(dvx, dvx), __dmul_rn(dvy, dvy)), __dmul_rn(dvz, dvz)));
+            const double E = __dadd_rn(ke, static_cast<double>(pe));
+            bound = (E <= 0.0) ? 1 : 0;           // :359 / :476 (NaN is neither bound nor unbound)
+            p.flag[i] = static_cast<uint8_t>(bound);
+            p.out_mask[g] = static_cast<uint8_t>(bound);
+            p.out_be[g] = be;
+            p.out_E[g] = E;
+            if (bound) {
+                const double m = p.m64[g];
+                s[0] = m;
+                s[1] = m * p.vx[g];
+                s[2] = m * p.vy[g];
+                s[3] = m * p.vz[g];
+                s[4] = m * p.x64[g];
+                s[5] = m * p.y64[g];
+                s[6] = m * p.z64[g];
+            }
+        }
+        const int count = __syncthreads_count(bound);
+        block_sum<7>(s, red);
+        if (threadIdx.x == 0) {
+            p.chunk_cnt[c] = count;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) p.chunk_sum[static_cast<int64_t>(c) * 7 + k] = s[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Per halo: exclusive scan of chunk counts, ordered reduction of the chunk sums, and the
+// convergence decision.  init = 1 right after k_pack_members (no pass made yet).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int init)
+{
+    __shared__ int sscan[kCh / 32 + 1];
+    __shared__ double red[7 * (kCh / 32)];
+    if (!init && !p.st->any_active) return;
+    for (int h = blockIdx.x; h < p.n_halo; h += gridDim.x) {
+        if (!init && !p.active[h]) continue;
+        const HaloDesc &hd = p.halo[h];
+        const int n_old = init ? hd.n0 : p.cnt[h];
+        const int nch = (n_old + kCh - 1) / kCh;
+        int carry = 0;
+        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int c0 = 0; c0 < nch; c0 += kCh) {
+            const int c = c0 + threadIdx.x;
+            const int v = (c < nch) ? p.chunk_cnt[hd.chunk_begin + c] : 0;
+            int total;
+            const int ex = block_exclusive_scan(v, sscan, total);
+            if (c < nch) {
+                p.chunk_off[hd.chunk_begin + c] = carry + ex;
+                const double *cs = p.chunk_sum + static_cast<int64_t>(hd.chunk_begin + c) * 7;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) s[k] += cs[k];
+            }
+            carry += total;
+        }
+        block_sum<7>(s, red);
+        if (threadIdx.x == 0) {
+            const int n_new = carry;
+            const double M = s[0];
+            p.hM[h] = M;
+            const double inv = M > 0.0 ? 1.0 / M : 0.0;
+            // halo_properties.py:39-43, 56-60: sums divided by M, zeros when M == 0
+            for (int k = 0; k < 3; ++k) {
+                p.hcom[3 * h + k] = M > 0.0 ? s[4 + k] / M : 0.0;
+                p.hvb_next[3 * h + k] = p.vb_fixed ? p.hvb[3 * h + k] : (M > 0.0 ? s[1 + k] / M : 0.0);
+            }
+            (void)inv;
+            p.cnt_next[h] = n_new;
+            int act;
+            if (init) {
+                p.iter[h] = 0;
+                p.converged[h] = (n_new == 0) ? 1 : 0;
+                p.pairs[h] = 0ull;
+                act = (n_new > 0 && p.max_iter > 0) ? 1 : 0;
+            } else {
+                const int it = p.iter[h] + 1;
+                p.iter[h] = it;
+                p.pairs[h] += static_cast<unsigned long long>(n_old) *
+                              static_cast<unsigned long long>(n_old + hd.n_ext);
+                const int changed = n_new != n_old;
+                p.converged[h] = (!changed || n_new == 0) ? 1 : 0;
+                act = (changed && n_new > 0 && it < p.max_iter) ? 1 : 0;
+            }
+            p.active_next[h] = act;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 3: stable stream compaction (ballot + popc inside a warp, warp offsets through
+// shared memory, chunk offsets from k_halo_decide).  Order-preserving, so the member
+// indices stay ascending like part_list[bound] (halo_properties.py:359-361).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCh) k_compact(const LoopParams p)
+{
+    __shared__ int woff[kCh / 32];
+    if (!p.st->any_active) return;
+    const int par = p.st->parity, nxt = par ^ 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+        const int h = p.chunk_halo[c];
+        if (!p.active[h]) continue;
+        const int n = p.cnt[h];
+        const int p0 = p.chunk_p0[c];
+        if (p0 >= n) continue;
+        const HaloDesc &hd = p.halo[h];
+        const int q = p0 + threadIdx.x;
+        const int64_t i = hd.poff + q;
+        const int f = (q < n) ? p.flag[i] : 0;
+        const unsigned ballot = __ballot_sync(0xffffffffu, f);
+        const int rank_in_warp = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) woff[warp] = __popc(ballot);
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += woff[w];
+        if (f) {
+            const int64_t d = hd.poff + p.chunk_off[c] + base + rank_in_warp;
+            p.wx[nxt][d] = p.wx[par][i];
+            p.wy[nxt][d] = p.wy[par][i];
+            p.wz[nxt][d] = p.wz[par][i];
+            p.wm[nxt][d] = p.wm[par][i];
+            p.widx[nxt][d] = p.widx[par][i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Commit per-halo state and build the ticket table of the next potential pass.
+// Single block.  Tickets are laid out in `order` (largest halo first).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
+{
+    __shared__ int sred[33];
+    __shared__ int s_total_groups, s_carry, s_any;
+    LoopState *st = p.st;
+    if (!init && !st->any_active) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // commit
+    int groups = 0, any = 0;
+    for (int h = threadIdx.x; h < p.n_halo; h += blockDim.x) {
+        if (init || p.active[h]) {
+            // the halo took part in this pass: its members now live in the other buffer
+            if (!init) p.halo_buf[h] = st->parity ^ 1;
+            p.cnt[h] = p.cnt_next[h];
+            p.active[h] = p.active_next[h];
+            for (int k = 0; k < 3; ++k) p.hvb[3 * h + k] = p.hvb_next[3 * h + k];
+        }
+        if (init) p.halo_buf[h] = 0;
+        if (p.active[h]) {
+            groups += my_groups(p.cnt[h], p.group_size, p.rank, p.n_ranks);
+            any = 1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) groups += __shfl_down_sync(0xffffffffu, groups, o);
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) sred[warp] = groups;
+    if (threadIdx.x == 0) {
+        s_any = 0;
+        s_carry = 0;
+    }
+    __syncthreads();
+    if (lane == 0 && any) atomicOr(&s_any, 1);
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += sred[w];
+        s_total_groups = t;
+    }
+    __syncthreads();
+    const int total_groups = s_total_groups;
+    int want = 1;
+    if (p.mode == HALMA_MODE_FAST && total_groups > 0 && total_groups < p.target_items)
+        want = (p.target_items + total_groups - 1) / total_groups;
+
+    // ticket counts in `order` space, tile-wise block scan with a running carry
+    int max_split = 1;
+    for (int k0 = 0; k0 < p.n_halo; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        int items = 0, h = -1;
+        if (k < p.n_halo) {
+            h = p.order[k];
+            if (p.active[h]) {
+                const int n = p.cnt[h];
+                const int n_src = n + p.halo[h].n_ext;
+                int S = min(want, min(p.max_split, max(1, n_src / kMinSplitSources)));
+                p.nsplit[h] = S;
+                max_split = max(max_split, S);
+                items = my_groups(n, p.group_size, p.rank, p.n_ranks) * S;
+            }
+        }
+        // inclusive warp scan
+        int incl = items;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        __syncthreads();
+        if (lane == 31) sred[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = sred[lane];
+            int wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += y;
+            }
+            sred[lane] = wi - w;
+            if (lane == 31) sred[32] = wi;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (k < p.n_halo) p.item_base[k] = carry + sred[warp] + incl - items;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + sred[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        p.item_base[p.n_halo] = s_carry;
+        st->n_items = s_carry;
+        st->any_active = s_any;
+        st->counter = 0u;
+        if (init) {
+            st->parity = 0;
+            st->pass = 0;
+        } else {
+            st->parity ^= 1;
+            st->pass += 1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) max_split = max(max_split, __shfl_down_sync(0xffffffffu, max_split, o));
+    if (lane == 0 && max_split > 1) atomicMax(&st->n_split, max_split);
+}
+
+// ---------------------------------------------------------------------------------------
+// Split mode: fold the j-split partials into plane 0 before the all-reduce, and clear the
+// entries this rank does not own (they are filled by the reduction with exact zeros added).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fold_partials(const LoopParams p)
+{
+    if (!p.st->any_active) return;
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+        const int h = p.chunk_halo[c];
+        if (!p.active[h]) continue;
+        const int n = p.cnt[h];
+        const int q = p.chunk_p0[c] + threadIdx.x;
+        if (q >= n) continue;
+        const int64_t i = p.halo[h].poff + q;
+        const int owner = (q / p.group_size) % p.n_ranks;
+        double phi = 0.0;
+        if (owner == p.rank) {
+            const int S = p.nsplit[h];
+            phi = p.phi_part[i];
+            for (int k = 1; k < S; ++k) phi += p.phi_part[static_cast<int64_t>(k) * p.n_pad + i];
+        }
+        p.phi_part[i] = phi;
+    }
+}
+
+// After the all-reduce plane 0 holds the complete Phi: tell k_energy_flag to read only it.
+__global__ void k_set_nsplit_one(const LoopParams p)
+{
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < p.n_halo; h += gridDim.x * blockDim.x)
+        p.nsplit[h] = 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// Final member lists: ascending local indices of the bound members of each halo.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCh) k_finalize(const LoopParams p)
+{
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+        const int h = p.chunk_halo[c];
+        const HaloDesc &hd = p.halo[h];
+        const int q = p.chunk_p0[c] + threadIdx.x;
+        if (q >= hd.n0) continue;
+        const int n = p.cnt[h];
+        const int b = p.halo_buf[h];
+        p.out_idx[hd.uoff + q] = (q < n) ? static_cast<int32_t>(p.widx[b][hd.poff + q] - hd.uoff) : -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host launchers
+// ---------------------------------------------------------------------------------------
+static inline int chunk_grid(const LoopParams &p, int sm_count)
+{
+    const int want = sm_count * 8;
+    return p.n_chunks < want ? (p.n_chunks > 0 ? p.n_chunks : 1) : want;
+}
+
+cudaError_t launch_pack_members(const LoopParams &p, int sm_count, cudaStream_t s)
+{
+    k_pack_members<<<chunk_grid(p, sm_count), kCh, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_group(const HaloDesc *halo, int n_halo, int seg_index, int max_count, const int64_t *ext_off,
+                              const double *m, const double *x, const double *y, const double *z, float *em,
+                              float *ex, float *ey, float *ez, cudaStream_t s)
+{
+    int gx = (max_count + 255) / 256;
+    gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+    int gy = n_halo < 1 ? 1 : (n_halo > 4096 ? 4096 : n_halo);
+    if (gx * gy > 65536) gx = 65536 / gy > 0 ? 65536 / gy : 1;
+    k_pack_group<<<dim3(gx, gy), 256, 0, s>>>(halo, n_halo, seg_index, ext_off, m, x, y, z, em, ex, ey, ez);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_energy_flag(const LoopParams &p, int sm_count, cudaStream_t s)
+{
+    k_energy_flag<<<chunk_grid(p, sm_count), kCh, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_decide(const LoopParams &p, int init, int sm_count, cudaStream_t s)
+{
+    const int want = sm_count * 8;
+    const int g = p.n_halo < want ? (p.n_halo > 0 ? p.n_halo : 1) : want;
+    k_halo_decide<<<g, kCh, 0, s>>>(p, init);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact(const LoopParams &p, int sm_count, cudaStream_t s)
+{
+    k_compact<<<chunk_grid(p, sm_count), kCh, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_schedule(const LoopParams &p, int init, cudaStream_t s)
+{
+    k_schedule<<<1, 1024, 0, s>>>(p, init);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold_partials(const LoopParams &p, int sm_count, cudaStream_t s)
+{
+    k_fold_partials<<<chunk_grid(p, sm_count), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_set_nsplit_one(const LoopParams &p, cudaStream_t s)
+{
+    const int g = (p.n_halo + 255) / 256;
+    k_set_nsplit_one<<<g < 1 ? 1 : g, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const LoopParams &p, int sm_count, cudaStream_t s)
+{
+    k_finalize<<<chunk_grid(p, sm_count), kCh, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace halma

@@ -1,0 +1,56 @@
+// Host-visible interface of loop_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/halma_unbind.h"
+#include "halma_common.cuh"
+
+namespace halma {
+
+constexpr int kChunk = 256;               // members per bookkeeping chunk
+constexpr int kMinSplitSources = 2048;    // never split a halo's sources into pieces below this
+constexpr int kMaxSplit = 8;              // planes of the partial-potential buffer
+
+struct LoopParams {
+    // static description
+    const HaloDesc *halo;
+    const int32_t *chunk_halo, *chunk_p0, *order;
+    int32_t n_halo, n_chunks;
+    int64_t n_pad, n_user;
+    // pristine float64 members in the user's layout
+    const double *x64, *y64, *z64, *vx, *vy, *vz, *m64;
+    // float32 working sets (ping-pong) + global user index of each slot
+    float *wx[2], *wy[2], *wz[2], *wm[2];
+    int32_t *widx[2];
+    // per-halo dynamic state
+    int32_t *cnt, *cnt_next, *iter, *active, *active_next, *halo_buf, *nsplit, *item_base, *converged;
+    double *hM, *hvb, *hvb_next, *hcom;
+    unsigned long long *pairs;
+    // per-chunk scratch
+    int32_t *chunk_cnt, *chunk_off;
+    double *chunk_sum;                    // 7 per chunk: m, m*v[3], m*x[3]
+    // per-particle
+    uint8_t *flag;                        // [n_pad] bound flag of the current pass
+    uint8_t *out_mask;                    // [n_user]
+    float *out_be;                        // [n_user]
+    double *out_E;                        // [n_user]
+    int32_t *out_idx;                     // [n_user]
+    double *phi_part;                     // [kMaxSplit][n_pad]
+    LoopState *st;
+    float G32, kappa32;
+    int32_t vb_fixed, max_iter, mode, group_size, rank, n_ranks, target_items, max_split;
+};
+
+cudaError_t launch_pack_members(const LoopParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_pack_group(const HaloDesc *halo, int n_halo, int seg_index, int max_count,
+                              const int64_t *ext_off, const double *m, const double *x, const double *y,
+                              const double *z, float *em, float *ex, float *ey, float *ez, cudaStream_t s);
+cudaError_t launch_energy_flag(const LoopParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_halo_decide(const LoopParams &p, int init, int sm_count, cudaStream_t s);
+cudaError_t launch_compact(const LoopParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_schedule(const LoopParams &p, int init, cudaStream_t s);
+cudaError_t launch_fold_partials(const LoopParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_set_nsplit_one(const LoopParams &p, cudaStream_t s);
+cudaError_t launch_finalize(const LoopParams &p, int sm_count, cudaStream_t s);
+
+}  // namespace halma

@@ -1,0 +1,258 @@
+"""Device-resident iterative unbinding: Python face of the halma_plan_* C-ABI.
+
+Semantics: each pass evaluates the reference's one-pass unbinding
+(python_scripts/halo_properties.py:333-361 for stars, python_scripts/halo_gas.py:299-476
+for gas) on the current member set, keeps the bound members in their original order, and
+repeats until the set stops changing.  `max_iter=1` with a fixed bulk velocity IS the
+reference function.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+G_CONST = (4.3 * 1e-3) * 1e-6          # halo_gas.py:459-460, halo_properties.py:345-346
+
+
+def _f64(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim != 1:
+        raise ValueError("expected a rank-1 array")
+    return a
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+@dataclass
+class RunStats:
+    total_ms: float
+    potential_ms: float
+    potential_launches: int
+    launches: int
+    passes: int
+    pairs: int
+
+
+@dataclass
+class HaloResult:
+    n_bound: int
+    n_iter: int
+    converged: bool
+    mass: float
+    com: tuple
+    vb: tuple
+    pairs: int
+
+
+@dataclass
+class CatalogueResult:
+    offsets: np.ndarray
+    mask: Optional[np.ndarray]
+    be32: Optional[np.ndarray]
+    energy: Optional[np.ndarray]
+    idx_packed: Optional[np.ndarray]
+    halos: List[HaloResult]
+    stats: Optional[RunStats] = None
+
+    def members(self, h: int) -> np.ndarray:
+        """Ascending local indices of the bound members of halo h."""
+        a = int(self.offsets[h])
+        return self.idx_packed[a:a + self.halos[h].n_bound]
+
+    def halo_mask(self, h: int) -> np.ndarray:
+        return self.mask[int(self.offsets[h]):int(self.offsets[h + 1])].astype(bool)
+
+
+@dataclass
+class UnbindResult:
+    """Single-halo result, field-compatible with oracle.UnbindResult."""
+    mask: np.ndarray
+    idx: np.ndarray
+    be32: np.ndarray
+    energy: np.ndarray
+    n_iter: int
+    mass: float
+    com: tuple
+    vb: tuple
+    pairs: int
+    converged: bool
+    stats: Optional[RunStats] = field(default=None, repr=False)
+
+
+class UnbindPlan:
+    """A batch of haloes resident on one GPU.
+
+    offsets: int64[n_halo+1] CSR over the concatenated member arrays.
+    ext_offsets: one int64[n_halo+1] per external source group.
+    Stellar layout (halo_properties.py:333-339): split_classes=False, groups[:n_pre] are
+    summed before the members (gas), the rest after (DM).  Gas layout (halo_gas.py:301-450):
+    split_classes=True, members (gas) first, then each group as its own float32 class.
+    """
+
+    def __init__(self, offsets, ext_offsets: Sequence = (), *, mode="fast", n_pre: int = 0,
+                 split_classes: bool = False, vb_fixed: bool = False, max_iter: int = 64,
+                 G: float = G_CONST, kappa: float = 9.0, device: int = 0, rank: int = 0, n_ranks: int = 1):
+        L = _lib.lib()
+        self._L = L
+        self.offsets = _i64(offsets)
+        if self.offsets.ndim != 1 or len(self.offsets) < 1:
+            raise ValueError("offsets must be int64[n_halo+1]")
+        self.n_halo = len(self.offsets) - 1
+        self.n = int(self.offsets[-1])
+        self.ext_offsets = [_i64(e) for e in ext_offsets]
+        for e in self.ext_offsets:
+            if e.shape != self.offsets.shape:
+                raise ValueError("every ext_offsets array must have n_halo+1 entries")
+        if len(self.ext_offsets) > _lib.MAX_GROUPS:
+            raise ValueError("at most %d external groups" % _lib.MAX_GROUPS)
+        cfg = _lib.UnbindConfig()
+        cfg.struct_size = C.sizeof(_lib.UnbindConfig)
+        cfg.device = device
+        cfg.mode = _lib.mode_code(mode)
+        cfg.n_groups = len(self.ext_offsets)
+        cfg.n_pre = n_pre
+        cfg.split_classes = int(bool(split_classes))
+        cfg.vb_fixed = int(bool(vb_fixed))
+        cfg.max_iter = int(max_iter)
+        cfg.G = float(G)
+        cfg.kappa = float(kappa)
+        cfg.rank = rank
+        cfg.n_ranks = n_ranks
+        self.cfg = cfg
+        ptrs = (C.POINTER(C.c_int64) * max(1, len(self.ext_offsets)))()
+        for g, e in enumerate(self.ext_offsets):
+            ptrs[g] = e.ctypes.data_as(C.POINTER(C.c_int64))
+        h = C.c_void_p()
+        _lib.check(L.halma_plan_create(C.byref(cfg), self.n_halo, self.offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                       ptrs, C.byref(h)))
+        self._h = h
+        self._keep = []      # host arrays referenced by in-flight copies
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.halma_plan_destroy(self._h)
+            self._h = None
+            self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- inputs ---------------------------------------------------------------------------
+    def upload_members(self, x, y, z, vx, vy, vz, mass):
+        arrs = [_f64(a) for a in (x, y, z, vx, vy, vz, mass)]
+        for a in arrs:
+            if len(a) != self.n:
+                raise ValueError("member arrays must have offsets[-1] = %d entries, got %d" % (self.n, len(a)))
+        self._keep.append(arrs)
+        _lib.check(self._L.halma_plan_upload_members(self._h, *[a.ctypes.data for a in arrs]))
+
+    def upload_group(self, group: int, mass, x, y, z):
+        arrs = [_f64(a) for a in (mass, x, y, z)]
+        n = int(self.ext_offsets[group][-1])
+        for a in arrs:
+            if len(a) != n:
+                raise ValueError("group %d arrays must have %d entries, got %d" % (group, n, len(a)))
+        self._keep.append(arrs)
+        _lib.check(self._L.halma_plan_upload_group(self._h, group, *[a.ctypes.data for a in arrs]))
+
+    def set_vb(self, vb):
+        vb = np.ascontiguousarray(vb, dtype=np.float64).reshape(-1)
+        if len(vb) != 3 * self.n_halo:
+            raise ValueError("vb must have 3*n_halo entries")
+        self._keep.append([vb])
+        _lib.check(self._L.halma_plan_set_vb(self._h, vb.ctypes.data))
+
+    def join(self, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _lib.check(self._L.halma_plan_join(self._h, buf))
+
+    # -- execution ------------------------------------------------------------------------
+    def run(self) -> RunStats:
+        st = _lib.RunStats()
+        _lib.check(self._L.halma_plan_run(self._h, C.byref(st)))
+        self._keep = []
+        return RunStats(st.total_ms, st.potential_ms, st.potential_launches, st.launches, st.passes, st.pairs)
+
+    def download(self, mask=True, be=True, energy=True, idx=True, halos=True) -> CatalogueResult:
+        n = self.n
+        m = np.zeros(n, np.uint8) if mask else None
+        b = np.zeros(n, np.float32) if be else None
+        e = np.zeros(n, np.float64) if energy else None
+        i = np.zeros(n, np.int32) if idx else None
+        hr = (_lib.HaloResult * max(1, self.n_halo))() if halos else None
+        _lib.check(self._L.halma_plan_download(
+            self._h, m.ctypes.data if mask else None, b.ctypes.data if be else None,
+            e.ctypes.data if energy else None, i.ctypes.data if idx else None, hr))
+        out = []
+        if halos:
+            for h in range(self.n_halo):
+                r = hr[h]
+                out.append(HaloResult(int(r.n_bound), int(r.n_iter), bool(r.converged), float(r.mass),
+                                      tuple(r.com), tuple(r.vb), int(r.pairs)))
+        return CatalogueResult(self.offsets, m, b, e, i, out)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().halma_nccl_unique_id(buf))
+    return buf.raw
+
+
+def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (), n_pre: int = 0,
+                     split_classes: bool = False, vb=None, kappa: float = 9.0, max_iter: int = 64,
+                     mode="fast", device: int = 0, G: float = G_CONST) -> CatalogueResult:
+    """Unbind every halo of a catalogue in one batched, device-resident run.
+
+    groups: sequence of (ext_offsets, mass, x, y, z) external source groups.
+    vb: None (bulk velocity recomputed from the bound set each pass) or float64[n_halo, 3].
+    """
+    plan = UnbindPlan(offsets, [g[0] for g in groups], mode=mode, n_pre=n_pre, split_classes=split_classes,
+                      vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa, device=device)
+    try:
+        plan.upload_members(x, y, z, vx, vy, vz, mass)
+        for k, g in enumerate(groups):
+            plan.upload_group(k, g[1], g[2], g[3], g[4])
+        if vb is not None:
+            plan.set_vb(vb)
+        stats = plan.run()
+        res = plan.download()
+        res.stats = stats
+        return res
+    finally:
+        plan.close()
+
+
+def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence = (),
+                split_classes: bool = False, kappa: float = 9.0, vb_fixed=None, max_iter: int = 64,
+                mode="fast", device: int = 0, G: float = G_CONST) -> UnbindResult:
+    """One halo.  pre / post: sequences of (mass, x, y, z) fixed source groups summed before /
+    after the members (same keywords as oracle.unbind_halo)."""
+    n = len(x)
+    if split_classes and len(pre):
+        raise ValueError("split_classes (gas layout) sums the members first: use post=")
+    ext = list(pre) + list(post)
+    groups = [(np.array([0, len(g[0])], np.int64), g[0], g[1], g[2], g[3]) for g in ext]
+    res = unbind_catalogue(np.array([0, n], np.int64), x, y, z, vx, vy, vz, mass, groups=groups,
+                           n_pre=len(pre), split_classes=split_classes,
+                           vb=None if vb_fixed is None else np.asarray(vb_fixed, np.float64).reshape(1, 3),
+                           kappa=kappa, max_iter=max_iter, mode=mode, device=device, G=G)
+    h = res.halos[0]
+    return UnbindResult(res.mask.astype(bool), res.members(0).astype(np.int64), res.be32, res.energy, h.n_iter,
+                        h.mass, h.com, h.vb, h.pairs, h.converged, res.stats)

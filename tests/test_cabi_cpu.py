@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/halma_unbind.h declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pyhalma_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "halma_unbind.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(halma_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "libhalma_unbind.so does not export %s" % n
+    assert set(names) == set(_lib.EXPORTS)
+
+
+def test_struct_sizes_match_header():
+    assert ctypes.sizeof(_lib.UnbindConfig) == 64
+    assert ctypes.sizeof(_lib.HaloResult) == 80
+    assert ctypes.sizeof(_lib.RunStats) == 40
+
+
+def test_abi_version():
+    assert _lib.lib().halma_abi_version() == 1
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from pyhalma_b200 import particle
+    with pytest.raises(_lib.HalmaError) as ei:
+        particle.brute_force_binding_energy(1, 2, np.ones(2), np.ones(2), np.ones(2), np.ones(2), 1, [0.], [0.], [0.])
+    assert ei.value.code == _lib.ERR_NO_DEVICE
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    assert L.halma_potential_f32(0, 7, None, None, None, None, 0, None, None, None, 0, None) == _lib.ERR_INVALID
+    assert L.halma_potential_f32(0, 0, None, None, None, None, -1, None, None, None, 0, None) == _lib.ERR_INVALID
+    assert L.halma_potential_f32(0, 0, None, None, None, None, 0, None, None, None, 0, None) == _lib.HALMA_OK
+    assert L.halma_potential_workspace_bytes(10, 10) >= 1024 + 8 * 12 * 8
+    cfg = _lib.UnbindConfig()
+    cfg.struct_size = 12          # wrong size -> ABI guard
+    h = ctypes.c_void_p()
+    off = (ctypes.c_int64 * 2)(0, 0)
+    assert L.halma_plan_create(ctypes.byref(cfg), 1, off, None, ctypes.byref(h)) == _lib.ERR_INVALID
+    assert b"size mismatch" in L.halma_last_error()
+
+
+def test_f2py_shape_errors():
+    from pyhalma_b200 import particle
+    with pytest.raises(ValueError):
+        particle.brute_force_binding_energy(1, 3, np.ones(2), np.ones(3), np.ones(3), np.ones(3), 1, [0.], [0.], [0.])
+    with pytest.raises(ValueError):
+        particle.serial_brute_force_binding_energy(2, np.ones(2), np.ones(2), np.ones(2), np.ones(2), 2, [0.], [0.], [0.])
+
+
+def test_wrapper_empty_targets_needs_no_gpu():
+    from pyhalma_b200 import halo_gas
+    out = halo_gas.brute_force_binding_energy_fortran(np.ones(3), np.ones(3), np.ones(3), np.ones(3), [], [], [])
+    assert out.shape == (0,) and out.dtype == np.float64        # halo_gas.py:169-170

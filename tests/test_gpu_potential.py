@@ -1,0 +1,158 @@
+"""GPU parity of the potential kernel against the CPU oracle, through the C-ABI.
+
+EXACT mode: bit-identical to the oracle's f32seq (the reference arithmetic).
+FAST mode: within 1e-6 relative of the oracle's f64acc (tolerance from BASELINE.json's
+north_star: "potentials ... must match within 1e-6 relative").
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from pyhalma_b200 import halo_gas, particle, synth
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+FAST_RTOL = 1e-6
+
+
+def gpu(m, x, y, z, tx, ty, tz, mode):
+    return particle.brute_force_binding_energy(1, len(m), f32(m), f32(x), f32(y), f32(z), len(tx), f32(tx),
+                                               f32(ty), f32(tz), mode=mode)
+
+
+def ora(m, x, y, z, tx, ty, tz, variant):
+    return O.brute_force_binding_energy(0, len(m), f32(m), f32(x), f32(y), f32(z), len(tx), f32(tx), f32(ty),
+                                        f32(tz), variant=variant)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_known_answers(mode):
+    out = gpu([26.0], [3.0], [4.0], [12.0], [0.0], [0.0], [0.0], mode)
+    assert out.dtype == np.float32 and abs(out[0] - 2.0) <= (0 if mode == "exact" else 4e-7)
+    m, x, y, z = [5.0, 7.0, 11.0], [1.0, 1.0, 2.0], [0.0, 3.0, 4.0], [0.0, 4.0, 12.0]
+    out = gpu(m, x, y, z, x, y, z, mode)
+    ref = ora(m, x, y, z, x, y, z, "f32seq")
+    if mode == "exact":
+        assert np.array_equal(bits(out), bits(ref))
+    else:
+        np.testing.assert_allclose(out, ref, rtol=FAST_RTOL)
+    m, x, y, z = [1.0, 1.0, 4.0], [0.5, 0.5, 1.5], [0.25, 0.25, 2.25], [0.125, 0.125, 2.125]
+    out = gpu(m, x, y, z, x, y, z, mode)
+    assert np.all(np.isfinite(out))
+    np.testing.assert_allclose(out, [4 / 3, 4 / 3, 2 / 3], rtol=FAST_RTOL)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_lattice_exclusion(mode):
+    n = 8
+    g = (np.arange(n) + 0.5) * 0.25
+    X, Y, Z = (a.ravel() for a in np.meshgrid(g, g, g, indexing="ij"))
+    m = np.ones(n ** 3)
+    out = gpu(m, X, Y, Z, X, Y, Z, mode)
+    if mode == "exact":
+        assert np.array_equal(bits(out), bits(ora(m, X, Y, Z, X, Y, Z, "f32seq")))
+    else:
+        np.testing.assert_allclose(out, ora(m, X, Y, Z, X, Y, Z, "f64acc"), rtol=FAST_RTOL)
+
+
+RAGGED = [(1, 1), (2, 1), (3, 5), (4, 31), (5, 32), (7, 33), (127, 127), (128, 128), (129, 129), (131, 257),
+          (255, 1), (256, 640), (257, 1000), (383, 77), (1000, 513), (4099, 300)]
+
+
+@pytest.mark.parametrize("n_src,n_tgt", RAGGED)
+def test_ragged_sizes_exact_and_fast(n_src, n_tgt):
+    rng = np.random.default_rng(n_src * 7919 + n_tgt)
+    p = synth.plummer_stars(n_src, 2e-3, 1e6, rng)
+    t = synth.plummer_stars(n_tgt, 2e-3, 1e6, rng)
+    k = min(n_src, n_tgt) // 2
+    t.x[:k], t.y[:k], t.z[:k] = p.x[:k], p.y[:k], p.z[:k]       # some targets are sources too
+    args = (p.mass, p.x, p.y, p.z, t.x, t.y, t.z)
+    assert np.array_equal(bits(gpu(*args, "exact")), bits(ora(*args, "f32seq")))
+    ref = ora(*args, "f64acc")
+    got = gpu(*args, "fast").astype(np.float64)
+    ok = ref > 0
+    assert np.all(got[~ok] == 0)
+    assert np.max(np.abs(got[ok] / ref[ok] - 1)) < FAST_RTOL
+
+
+def test_cfg1_stars_and_gas_exact_bit_parity():
+    c = synth.config1()
+    s, g, d = c.stars, c.gas, c.dm
+    src = [np.concatenate((getattr(g, k), getattr(s, k), getattr(d, k))) for k in ("mass", "x", "y", "z")]
+    out = gpu(*src, s.x, s.y, s.z, "exact")
+    ref = ora(*src, s.x, s.y, s.z, "f32seq")
+    assert np.array_equal(bits(out), bits(ref))
+    out = gpu(g.mass, g.x, g.y, g.z, g.x, g.y, g.z, "exact")        # lattice gas: ~13 % pairs excluded
+    ref = ora(g.mass, g.x, g.y, g.z, g.x, g.y, g.z, "f32seq")
+    assert np.array_equal(bits(out), bits(ref))
+
+
+def test_cfg1_fast_within_tolerance():
+    c = synth.config1()
+    s, g, d = c.stars, c.gas, c.dm
+    src = [np.concatenate((getattr(g, k), getattr(s, k), getattr(d, k))) for k in ("mass", "x", "y", "z")]
+    for tgt in (s, g):
+        got = gpu(*src, tgt.x, tgt.y, tgt.z, "fast").astype(np.float64)
+        ref = ora(*src, tgt.x, tgt.y, tgt.z, "f64acc")
+        err = np.abs(got / ref - 1)
+        assert err.max() < FAST_RTOL, err.max()
+        # and the drift of the reference's own float32 sum against the same anchor, for the record
+        drift = np.abs(ora(*src, tgt.x, tgt.y, tgt.z, "f32seq") / ref - 1).max()
+        assert drift < 1e-4
+
+
+def test_cfg2_full_size_fast_sampled_check_and_linearity():
+    # BASELINE cfg2 sizes: 2e5 star targets against 7e5 sources; the oracle checks a sample
+    c = synth.config2()
+    s, g = c.stars, c.gas
+    src = [np.concatenate((getattr(g, k), getattr(s, k))) for k in ("mass", "x", "y", "z")]
+    got = gpu(*src, s.x, s.y, s.z, "fast")
+    pick = np.random.default_rng(1).choice(len(s), 256, replace=False)
+    ref = ora(*src, s.x[pick], s.y[pick], s.z[pick], "f64acc")
+    assert np.max(np.abs(got[pick].astype(np.float64) / ref - 1)) < FAST_RTOL
+    # linearity: scaling every mass by 4 scales Phi by exactly 4 (power of two)
+    got4 = gpu(src[0] * 4, src[1], src[2], src[3], s.x[:50_000], s.y[:50_000], s.z[:50_000], "fast")
+    assert np.array_equal(bits(got4), bits(got[:50_000] * f32(4)))
+    # additivity over a source partition, in float64 tolerance
+    a = gpu(g.mass, g.x, g.y, g.z, s.x[:20_000], s.y[:20_000], s.z[:20_000], "fast").astype(np.float64)
+    b = gpu(s.mass, s.x, s.y, s.z, s.x[:20_000], s.y[:20_000], s.z[:20_000], "fast").astype(np.float64)
+    np.testing.assert_allclose(a + b, got[:20_000], rtol=5e-7)
+
+
+def test_empty_inputs():
+    out = particle.brute_force_binding_energy(1, 0, f32([]), f32([]), f32([]), f32([]), 3, f32([1, 2, 3]),
+                                              f32([1, 2, 3]), f32([1, 2, 3]))
+    assert out.shape == (3,) and np.all(out == 0)
+    out = particle.brute_force_binding_energy(1, 2, f32([1, 1]), f32([1, 2]), f32([1, 2]), f32([1, 2]), 0, f32([]),
+                                              f32([]), f32([]))
+    assert out.shape == (0,)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_wrapper_mirror_float64_inputs(mode):
+    rng = np.random.default_rng(3)
+    p = synth.plummer_stars(700, 2e-3, 1e6, rng)
+    got = halo_gas.brute_force_binding_energy_fortran(p.mass, p.x, p.y, p.z, p.x[:99], p.y[:99], p.z[:99], mode=mode)
+    ref = O.brute_force_binding_energy_fortran(p.mass, p.x, p.y, p.z, p.x[:99], p.y[:99], p.z[:99],
+                                               variant="f32seq" if mode == "exact" else "f64acc")
+    assert got.dtype == np.float32
+    if mode == "exact":
+        assert np.array_equal(bits(got), bits(ref))
+    else:
+        np.testing.assert_allclose(got, ref, rtol=FAST_RTOL)
+    ser = halo_gas.serial_brute_force_binding_energy_fortran(p.mass, p.x, p.y, p.z, p.x[:99], p.y[:99], p.z[:99],
+                                                             mode=mode)
+    assert np.array_equal(bits(ser), bits(got))
+
+
+def test_nan_inf_semantics_exact():
+    out = gpu([1.0, 1.0], [np.nan, 5.0], [1.0, 0.0], [1.0, 7.0], [0.0], [0.0], [0.0], "exact")
+    assert np.isnan(out[0])
+    out = gpu([1.0, 1.0], [np.nan, 5.0], [0.0, 3.0], [1.0, 7.0], [0.0], [0.0], [0.0], "exact")
+    assert out[0] == f32(1.0) / np.sqrt(f32(83.0))
+    out = gpu([1.0], [np.inf], [1.0], [1.0], [0.0], [0.0], [0.0], "exact")
+    assert out[0] == 0.0
