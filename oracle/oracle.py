@@ -446,7 +446,8 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence[SourceGroup] = (),
 def energy_margin(E: np.ndarray, be32: np.ndarray, kappa: float) -> np.ndarray:
     """|E| / max(KE, |PE|): the relative distance from the E = 0 boundary used to bin mask
     differences (SURVEY.md §7 hard part 1; north_star's 1e-6 band)."""
-    pe = np.abs(np.float64(np.float32(np.float32(be32) * np.float32(G_const())) * np.float32(kappa)))
+    pe = np.abs((np.float32(np.asarray(be32, np.float32) * np.float32(G_const()))
+                 * np.float32(kappa)).astype(np.float64))
     ke = np.abs(E + pe)
     scale = np.maximum(ke, pe)
     with np.errstate(divide="ignore", invalid="ignore"):

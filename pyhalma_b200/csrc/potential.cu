@@ -19,6 +19,8 @@
 // EXACT kernel: one target per thread, sources strictly in ascending order, IEEE sqrt and
 // divide, the reference's != predicate, float32 accumulator: bit-identical to the reference
 // arithmetic (see oracle/halma_oracle.c for the contraction of r^2).
+#include <cstdlib>
+
 #include "halma_common.cuh"
 #include "potential.h"
 
@@ -206,8 +208,8 @@ __device__ __forceinline__ void tile_fast(const float *__restrict__ stage, int l
     }
 }
 
-template <int T>
-__global__ void __launch_bounds__(kPotentialBlock, 4) k_potential_fast(const PotParams p)
+template <int T, int MINB>
+__global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const PotParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LoopState *st = p.st;
@@ -401,7 +403,37 @@ __global__ void __launch_bounds__(kPotentialBlock, 4) k_potential_exact(const Po
 // ---------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------
-int potential_group_size(int mode) { return mode == HALMA_MODE_EXACT ? 32 : 32 * kFastTargets; }
+namespace {
+
+// Shapes of the FAST kernel: T targets per lane (group = 32 T targets per ticket) and the
+// minimum resident blocks per SM the register allocation is held to.  Variant 0 is the
+// default; HALMA_FAST_VARIANT=<index> selects another one (tuning sweeps).
+struct FastVariant {
+    int targets, min_blocks;
+    void (*kernel)(const PotParams);
+};
+
+const FastVariant kVariants[] = {
+    {4, 6, k_potential_fast<4, 6>}, {4, 5, k_potential_fast<4, 5>}, {4, 4, k_potential_fast<4, 4>},
+    {2, 8, k_potential_fast<2, 8>}, {2, 6, k_potential_fast<2, 6>}, {3, 5, k_potential_fast<3, 5>},
+    {3, 6, k_potential_fast<3, 6>}, {6, 3, k_potential_fast<6, 3>}, {8, 2, k_potential_fast<8, 2>},
+    {2, 10, k_potential_fast<2, 10>}, {1, 12, k_potential_fast<1, 12>},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+const FastVariant &fast_variant()
+{
+    static int idx = [] {
+        const char *e = getenv("HALMA_FAST_VARIANT");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 0 && v < kNumVariants) ? v : 0;
+    }();
+    return kVariants[idx];
+}
+
+}  // namespace
+
+int potential_group_size(int mode) { return mode == HALMA_MODE_EXACT ? 32 : 32 * fast_variant().targets; }
 
 cudaError_t potential_configure(int mode, int *blocks_per_sm)
 {
@@ -412,11 +444,10 @@ cudaError_t potential_configure(int mode, int *blocks_per_sm)
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_potential_exact, kPotentialBlock,
                                                              kSmemBytes);
     }
-    e = cudaFuncSetAttribute(k_potential_fast<kFastTargets>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kSmemBytes);
+    const FastVariant &v = fast_variant();
+    e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_potential_fast<kFastTargets>,
-                                                         kPotentialBlock, kSmemBytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, v.kernel, kPotentialBlock, kSmemBytes);
 }
 
 cudaError_t potential_launch(const PotParams &p, int mode, int grid_blocks, cudaStream_t stream)
@@ -424,7 +455,7 @@ cudaError_t potential_launch(const PotParams &p, int mode, int grid_blocks, cuda
     if (mode == HALMA_MODE_EXACT)
         k_potential_exact<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else
-        k_potential_fast<kFastTargets><<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
+        fast_variant().kernel<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 

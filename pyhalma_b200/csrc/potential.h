@@ -8,9 +8,8 @@
 namespace halma {
 
 constexpr int kPotentialBlock = 128;     // 4 warps; each warp schedules itself
-constexpr int kFastTargets = 4;          // targets per lane in the FAST kernel
 
-// Targets per work item (warp): 32 (EXACT) or 32 * kFastTargets (FAST).
+// Targets per work item (warp): 32 (EXACT) or 32 * T (FAST, T = targets per lane of the variant).
 int potential_group_size(int mode);
 // Sets the dynamic shared-memory attribute and returns resident blocks per SM.
 cudaError_t potential_configure(int mode, int *blocks_per_sm);

@@ -124,6 +124,10 @@ def lattice_gas(n_target: int, spacing: float, rng, centre=CENTRE, bulk_v=BULK_V
     predicate (particle_subroutines.f90:499-501).  Masses follow a beta profile, T is
     log-uniform 1e3..1e7 K, velocities are bulk + Gaussian + a wind on half the cells.
     two_levels: the inner half (by radius) sits on `spacing`, the rest on 2*spacing."""
+    if n_target <= 0:
+        e = np.zeros(0)
+        return Particles(e, e.copy(), e.copy(), e.copy(), e.copy(), e.copy(), e.copy(), e.copy())
+
     def ball(n_cells, h, rmin=0.0, rmax=None):
         if rmax is None:
             vol = n_cells * h ** 3 + 4.0 / 3 * np.pi * rmin ** 3

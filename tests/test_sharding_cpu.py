@@ -1,0 +1,91 @@
+"""Host-side multi-GPU logic on CPU: LPT cost sharding and the world_size-2 gather (gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from pyhalma_b200 import sharding, synth
+
+
+def test_lpt_partition_properties():
+    rng = np.random.default_rng(0)
+    sizes = synth.powerlaw_sizes(10_000, 100, 100_000, 1.9, rng)
+    off = np.concatenate(([0], np.cumsum(sizes)))
+    costs = sharding.halo_costs(off)
+    assert costs.shape == (10_000,) and np.all(costs == sizes.astype(float) ** 2)
+    for n in (1, 2, 4, 8):
+        parts = sharding.lpt_partition(costs, n)
+        allids = np.concatenate(parts)
+        assert len(allids) == 10_000 and len(np.unique(allids)) == 10_000
+        assert all(np.all(np.diff(p) > 0) for p in parts)
+        # near-linear scaling needs a balanced split (largest halo < total/8)
+        assert sharding.partition_imbalance(costs, parts) < 1.02, n
+    assert sharding.lpt_partition(costs, 4)[2].tolist() == sharding.lpt_partition(costs.copy(), 4)[2].tolist()
+
+
+def test_lpt_edge_cases():
+    assert [p.tolist() for p in sharding.lpt_partition([], 3)] == [[], [], []]
+    parts = sharding.lpt_partition([5.0], 4)
+    assert sum(len(p) for p in parts) == 1
+    parts = sharding.lpt_partition([1, 1, 1, 1], 2)
+    assert sorted(len(p) for p in parts) == [2, 2]
+    costs = sharding.halo_costs([0, 10, 10, 14], [[0, 5, 5, 6]])
+    assert costs.tolist() == [10 * 15, 0, 4 * 5]
+
+
+def test_take_haloes_and_split_owner():
+    off = np.array([0, 3, 3, 7, 9])
+    x = np.arange(9.0)
+    o2, (x2,) = sharding.take_haloes(off, [x], [2, 0])
+    assert o2.tolist() == [0, 4, 7] and x2.tolist() == [3, 4, 5, 6, 0, 1, 2]
+    o3, (x3,) = sharding.take_haloes(off, [x], [])
+    assert o3.tolist() == [0] and len(x3) == 0
+    own = sharding.split_owner(1000, 128, 3)
+    assert own[0] == 0 and own[127] == 0 and own[128] == 1 and own[256] == 2 and own[384] == 0
+    counts = np.bincount(sharding.split_owner(2_000_000, 128, 8), minlength=8)
+    assert counts.max() - counts.min() <= 128
+
+
+def _worker(rank, world, port, n_halo, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(42)                 # same catalogue on every rank
+        sizes = synth.powerlaw_sizes(n_halo, 10, 5000, 1.9, rng)
+        off = np.concatenate(([0], np.cumsum(sizes)))
+        parts = sharding.lpt_partition(sharding.halo_costs(off), world)
+        mine = parts[rank]
+        sub_off, _ = sharding.take_haloes(off, [], mine)
+        # stand-in for the per-rank GPU run: rows = (size, size^2, rank)
+        n = np.diff(sub_off).astype(float)
+        rows = np.stack([n, n * n, np.full(len(n), float(rank))], axis=1) if len(n) else np.zeros((0, 3))
+        full = sharding.gather_catalogue(mine, rows, n_halo)
+        if rank == 0:
+            ok = (full is not None and np.array_equal(full[:, 0], sizes.astype(float))
+                  and set(np.unique(full[:, 2])) == set(range(world)))
+            q.put(bool(ok))
+        else:
+            q.put(full is None)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 200, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(results)
