@@ -46,52 +46,86 @@ UNIT = "Ginteractions/s"
 # ----------------------------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------------------------
-def make_workload(name: str, rank: int):
-    """Returns a list of jobs; a job = dict(kind, members, groups, kw) describing one plan."""
-    from pyhalma_b200 import synth
+def make_workload(name: str, rank: int, world: int = 1):
+    """Returns (jobs, desc, scaling).  A job describes one plan: CSR offsets, member arrays,
+    external groups (ext_offsets, mass, x, y, z), layout keywords, and whether the halo is
+    shared by all ranks (split mode)."""
+    from pyhalma_b200 import sharding, synth
+
+    def single(n):
+        return np.array([0, n], np.int64)
 
     def star_gas_jobs(case):
         s, g, d = case.stars, case.gas, case.dm
         M = float(np.sum(s.mass))
         vb = np.array([np.sum(s.mass * s.vx), np.sum(s.mass * s.vy), np.sum(s.mass * s.vz)]) / M
-        jobs = [dict(kind="stellar", members=(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass),
-                     groups=[(g.mass, g.x, g.y, g.z)] + ([(d.mass, d.x, d.y, d.z)] if len(d) else []),
+        grp = lambda p: (single(len(p)), p.mass, p.x, p.y, p.z)  # noqa: E731
+        jobs = [dict(kind="stellar", offsets=single(len(s)), members=(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass),
+                     groups=[grp(g)] + ([grp(d)] if len(d) else []), split=False,
                      kw=dict(n_pre=1, split_classes=False, vb=None, kappa=case.factor_v ** 2)),
-                dict(kind="gas", members=(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass),
-                     groups=([(d.mass, d.x, d.y, d.z)] if len(d) else []) + [(s.mass, s.x, s.y, s.z)],
+                dict(kind="gas", offsets=single(len(g)), members=(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass),
+                     groups=([grp(d)] if len(d) else []) + [grp(s)], split=False,
                      kw=dict(n_pre=0, split_classes=True, vb=vb, kappa=2.0))]
         return jobs
 
-    if name == "cfg2":
-        case = synth.config2(seed_extra=rank)
-        desc = {"workload": "cfg2: NFW galaxy halo, 2e5 stars + 5e5 gas cells per GPU, iterative stellar + gas "
-                            "unbinding", "n_star": len(case.stars), "n_gas": len(case.gas)}
-        return star_gas_jobs(case), desc
-    if name == "cfg1":
-        case = synth.config1(seed_extra=rank)
-        desc = {"workload": "cfg1: Plummer halo, 1e4 stars + 1e4 gas cells per GPU, iterative stellar + gas "
-                            "unbinding", "n_star": len(case.stars), "n_gas": len(case.gas)}
-        return star_gas_jobs(case), desc
+    if name in ("cfg2", "cfg1"):
+        case = synth.config2(seed_extra=rank) if name == "cfg2" else synth.config1(seed_extra=rank)
+        what = ("cfg2: NFW galaxy halo, 2e5 stars + 5e5 gas cells per GPU" if name == "cfg2"
+                else "cfg1: Plummer halo, 1e4 stars + 1e4 gas cells per GPU")
+        desc = {"workload": what + ", iterative stellar + gas unbinding", "n_star": len(case.stars),
+                "n_gas": len(case.gas), "parallelism": "1 halo per GPU, no collective"}
+        return star_gas_jobs(case), desc, "weak"
+    if name == "cfg3":
+        cat = synth.config3()                       # the same catalogue on every rank
+        parts = sharding.lpt_partition(sharding.halo_costs(cat.offsets), world)
+        off, cols = sharding.take_haloes(cat.offsets, [cat.x, cat.y, cat.z, cat.vx, cat.vy, cat.vz, cat.mass],
+                                         parts[rank])
+        desc = {"workload": "cfg3: catalogue of 1e4 Plummer haloes, N = 1e2..1e5 (dN/dN ~ N^-1.9), batched launch, "
+                            "iterative stellar unbinding", "n_halo": cat.n_halo, "sum_n": int(cat.offsets[-1]),
+                "sum_n2": cat.meta["sum_n2"], "halos_this_rank": int(len(parts[rank])),
+                "lpt_imbalance": sharding.partition_imbalance(sharding.halo_costs(cat.offsets), parts),
+                "parallelism": "haloes LPT-sharded by N^2 over %d GPU(s), no collective" % world}
+        jobs = [dict(kind="catalogue", offsets=off, members=tuple(cols), groups=[], split=False,
+                     kw=dict(n_pre=0, split_classes=False, vb=None, kappa=9.0))]
+        return jobs, desc, "strong"
+    if name == "cfg4":
+        n = int(os.environ.get("HALMA_CFG4_N", "2000000"))
+        p = synth.config4(n)                        # the same halo on every rank
+        desc = {"workload": "cfg4: one cluster-scale stellar halo, N = %d, targets split over the GPUs, one NCCL "
+                            "all-reduce of the potentials per pass" % n, "n_star": n,
+                "parallelism": "target groups round-robin over %d GPU(s), sources replicated" % world}
+        jobs = [dict(kind="giant", offsets=single(n), members=(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass), groups=[],
+                     split=world > 1, kw=dict(n_pre=0, split_classes=False, vb=None, kappa=9.0))]
+        return jobs, desc, "strong"
     raise SystemExit("unknown workload %r" % name)
 
 
-def job_offsets(job):
-    n = len(job["members"][0])
-    return np.array([0, n], np.int64), [np.array([0, len(g[0])], np.int64) for g in job["groups"]]
+_UID_CACHE = {}
 
 
-def make_plan(job, mode, device):
-    from pyhalma_b200.unbind import UnbindPlan
-    off, eoff = job_offsets(job)
+def make_plan(job, mode, device, rank=0, world=1, upload=True):
+    from pyhalma_b200.unbind import UnbindPlan, nccl_unique_id
     kw = job["kw"]
-    plan = UnbindPlan(off, eoff, mode=mode, n_pre=kw["n_pre"], split_classes=kw["split_classes"],
-                      vb_fixed=kw["vb"] is not None, max_iter=64, kappa=kw["kappa"], device=device)
+    split = job["split"] and world > 1
+    plan = UnbindPlan(job["offsets"], [g[0] for g in job["groups"]], mode=mode, n_pre=kw["n_pre"],
+                      split_classes=kw["split_classes"], vb_fixed=kw["vb"] is not None, max_iter=64,
+                      kappa=kw["kappa"], device=device, rank=rank if split else 0, n_ranks=world if split else 1)
+    if split:
+        import torch.distributed as dist
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        plan.join(uid[0])
+    if upload:
+        upload_job(plan, job)
+    return plan
+
+
+def upload_job(plan, job):
     plan.upload_members(*job["members"])
     for k, g in enumerate(job["groups"]):
-        plan.upload_group(k, *g)
-    if kw["vb"] is not None:
-        plan.set_vb(kw["vb"])
-    return plan
+        plan.upload_group(k, *g[1:])
+    if job["kw"]["vb"] is not None:
+        plan.set_vb(job["kw"]["vb"])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -148,29 +182,26 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 def cpu_sample(jobs, n_targets: int):
     """Times the oracle's f32seq kernel on a contiguous slice of `n_targets` targets of every
-    job against that job's full source set (first pass of the loop).  Cost is strictly
-    ntest x ntotal, so the rate carries over to the whole workload."""
+    job (of its largest halo) against that halo's full source set (first pass of the loop).
+    Cost is strictly ntest x ntotal, so the rate carries over to the whole workload."""
     from oracle import oracle as O
     f32 = np.float32
     pairs, secs = 0, 0.0
     threads = O.max_threads()
     for job in jobs:
-        x, y, z, _, _, _, m = job["members"]
-        src = [np.concatenate([m] + [g[0] for g in job["groups"]]),
-               np.concatenate([x] + [g[1] for g in job["groups"]]),
-               np.concatenate([y] + [g[2] for g in job["groups"]]),
-               np.concatenate([z] + [g[3] for g in job["groups"]])]
-        src = [f32(a) for a in src]
+        off = job["offsets"]
+        h = int(np.argmax(np.diff(off)))
+        a, b = int(off[h]), int(off[h + 1])
+        x, y, z, _, _, _, m = [c[a:b] for c in job["members"]]
+        ext = [tuple(arr[int(g[0][h]):int(g[0][h + 1])] for arr in g[1:]) for g in job["groups"]]
+        src = [f32(np.concatenate([m] + [e[0] for e in ext])), f32(np.concatenate([x] + [e[1] for e in ext])),
+               f32(np.concatenate([y] + [e[2] for e in ext])), f32(np.concatenate([z] + [e[3] for e in ext]))]
         nt = min(n_targets, len(x))
-        tgt = [f32(a[:nt]) for a in (x, y, z)]
-        best = None
-        for _ in range(1):
-            t0 = time.perf_counter()
-            O.brute_force_binding_energy(threads, len(src[0]), *src, nt, *tgt)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
+        tgt = [f32(c[:nt]) for c in (x, y, z)]
+        t0 = time.perf_counter()
+        O.brute_force_binding_energy(threads, len(src[0]), *src, nt, *tgt)
+        secs += time.perf_counter() - t0
         pairs += nt * len(src[0])
-        secs += best
     return pairs, secs, threads
 
 
@@ -179,7 +210,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     os.environ.setdefault("OMP_WAIT_POLICY", "active")       # run.sh:3
-    jobs, desc = make_workload(args.workload, 0)
+    jobs, desc, scaling = make_workload(args.workload, 0, 1)
     n_t = args.ref_targets
     for _ in range(args.warmup):
         cpu_sample(jobs, max(256, n_t // 8))
@@ -189,11 +220,10 @@ def run_reference(args, rank, world):
         pairs += p
         secs += s
     val = pairs / secs / 1e9
-    sample = "per step: first %d targets of each job (stars, gas) x all %s sources, float32 in-order sum" % (
-        n_t, "+".join(str(len(j["members"][0]) + sum(len(g[0]) for g in j["groups"])) for j in jobs))
+    sample = "per step: first %d targets of each job's largest halo x all its sources, float32 in-order sum" % n_t
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": desc,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,22 +247,20 @@ def pinned_copy(arr):
     return out
 
 
-def e2e_step(jobs_pinned, mode, device):
-    """One step through the public one-shot API: create, H2D, run, D2H, destroy."""
-    from pyhalma_b200.unbind import unbind_catalogue
+def e2e_step(jobs_pinned, mode, device, rank=0, world=1):
+    """One step through the public plan API from host buffers: create, H2D, run, D2H, destroy."""
     pairs = h2d = d2h = 0
     for job in jobs_pinned:
-        off, eoff = job_offsets(job)
-        groups = [(eo,) + tuple(g) for eo, g in zip(eoff, job["groups"])]
-        kw = job["kw"]
-        res = unbind_catalogue(off, *job["members"], groups=groups, n_pre=kw["n_pre"],
-                               split_classes=kw["split_classes"],
-                               vb=None if kw["vb"] is None else np.asarray(kw["vb"]).reshape(1, 3),
-                               kappa=kw["kappa"], mode=mode, device=device)
+        plan = make_plan(job, mode, device, rank, world, upload=True)
+        try:
+            st = plan.run()
+            plan.download()
+        finally:
+            plan.close()
         n = len(job["members"][0])
-        pairs += res.stats.pairs
-        h2d += 7 * 8 * n + sum(4 * 8 * len(g[0]) for g in job["groups"])
-        d2h += n * (1 + 4 + 8 + 4) + 80
+        pairs += st.pairs
+        h2d += 7 * 8 * n + sum(4 * 8 * len(g[1]) for g in job["groups"])
+        d2h += n * (1 + 4 + 8 + 4) + 80 * (len(job["offsets"]) - 1)
     return pairs, h2d, d2h
 
 
@@ -247,8 +275,8 @@ def run_gpu(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.require_device(local_rank)
     mode = args.mode
-    jobs, desc = make_workload(args.workload, rank)
-    plans = [make_plan(j, mode, local_rank) for j in jobs]
+    jobs, desc, scaling = make_workload(args.workload, rank, world)
+    plans = [make_plan(j, mode, local_rank, rank, world) for j in jobs]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -293,15 +321,15 @@ def run_gpu(args, rank, local_rank, world):
     # e2e: public one-shot API from pinned host buffers
     jobs_pinned = []
     for j in jobs:
-        jobs_pinned.append(dict(kind=j["kind"], members=tuple(pinned_copy(a) for a in j["members"]),
-                                groups=[tuple(pinned_copy(a) for a in g) for g in j["groups"]], kw=j["kw"]))
-    e2e_step(jobs_pinned, mode, local_rank)
+        jobs_pinned.append(dict(j, members=tuple(pinned_copy(a) for a in j["members"]),
+                                groups=[(g[0],) + tuple(pinned_copy(a) for a in g[1:]) for g in j["groups"]]))
+    e2e_step(jobs_pinned, mode, local_rank, rank, world)
     barrier()
     te0 = time.perf_counter()
     e2e_pairs = 0
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
-        p_, h2d, d2h = e2e_step(jobs_pinned, mode, local_rank)
+        p_, h2d, d2h = e2e_step(jobs_pinned, mode, local_rank, rank, world)
         e2e_pairs += p_
     barrier()
     e2e_s = time.perf_counter() - te0
@@ -326,7 +354,7 @@ def run_gpu(args, rank, local_rank, world):
         pot_rate = pairs / (pot_ms * 1e-3) / 1e9
         sm_mhz = clocks.get("sm_mhz") or mb["sm_clock_mhz"]
         peak = mb["rsq_per_clk_sm"] * mb["sm_count"] * sm_mhz * 1e6 / 1e9
-        n_src = [len(j["members"][0]) + sum(len(g[0]) for g in j["groups"]) for j in jobs]
+        n_src = [len(j["members"][0]) + sum(len(g[1]) for g in j["groups"]) for j in jobs]
         n_tgt = [len(j["members"][0]) for j in jobs]
         alg_bytes_first_pass = sum(16 * s + 12 * t_ + 8 * t_ for s, t_ in zip(n_src, n_tgt))
         roofline = {
@@ -351,16 +379,16 @@ def run_gpu(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(desc, mode=mode, l2="flushed between steps (256 MiB write)",
-                           passes_per_step=passes / args.steps, parallelism="1 halo per GPU, no collective"),
+                           passes_per_step=passes / args.steps),
             "wall_ms_per_step": wall_ms_max / args.steps,
             "interactions_per_step": pairs_all / args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_pairs_all / e2e_s_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "how": "pyhalma_b200.unbind_catalogue one-shot per job: plan create + H2D from pinned host + "
-                           "device loop + D2H of mask, potentials, energies, member lists"},
+                    "how": "public plan API per job, everything inside the timing: plan create + H2D from pinned "
+                           "host + device loop + D2H of mask, potentials, energies, member lists + destroy"},
             "gpu_launches": int(launches_all),
             "roofline": roofline,
             "cpu_baseline": cpu,

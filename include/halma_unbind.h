@@ -196,7 +196,8 @@ int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n,
  * Pipe-rate microbenchmark used for the roofline denominator: measures
  * MUFU.RSQ, FFMA and packed FFMA2 issue rates per SM per clock, and the SM clock during
  * the measurement.  out: double[8] = {rsq_per_clk_sm, ffma_per_clk_sm, ffma2_per_clk_sm,
- * sm_clock_mhz, sm_count, 0, 0, 0}.
+ * sm_clock_mhz (clock64 vs globaltimer inside the kernel), sm_count, and the absolute
+ * rates rsq, ffma, ffma2 in 1e9 thread-instructions per second}.
  * ------------------------------------------------------------------------------------ */
 int halma_microbench(int device, double *out8);
 

@@ -127,7 +127,25 @@ def microbench(device: int = 0) -> dict:
     out = (C.c_double * 8)()
     check(lib().halma_microbench(device, out))
     return {"rsq_per_clk_sm": out[0], "ffma_per_clk_sm": out[1], "ffma2_per_clk_sm": out[2],
-            "sm_clock_mhz": out[3], "sm_count": int(out[4])}
+            "sm_clock_mhz": out[3], "sm_count": int(out[4]), "rsq_gops": out[5], "ffma_gops": out[6],
+            "ffma2_gops": out[7]}
+
+
+def ensure_nccl_path() -> None:
+    """Point libhalma_unbind at the NCCL build torch ships (split mode only).  Found without
+    importing torch; an explicit HALMA_NCCL_LIB wins."""
+    if os.environ.get("HALMA_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["HALMA_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
 
 
 def mode_code(mode) -> int:

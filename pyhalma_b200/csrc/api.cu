@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -220,8 +221,7 @@ static int potential_dev(DeviceCtx *c, int mode, const float *sm, const float *s
     }
     const int group = potential_group_size(mode);
     const int grid = c->sm_count * c->bps[mode];
-    const int target_items = 8 * grid * (kPotentialBlock / 32);
-    const int S = choose_split(mode, n_tgt, n_src, group, target_items);
+    const int S = choose_split(mode, n_tgt, n_src, group, kNominalTickets);
     const int64_t groups = (n_tgt + group - 1) / group;
 
     PotWorkspaceHeader hdr;
@@ -360,8 +360,13 @@ static int load_nccl()
 {
     std::lock_guard<std::mutex> lock(g_nccl_mu);
     if (g_nccl.handle) return HALMA_OK;
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    // HALMA_NCCL_LIB lets the host side point at the NCCL build it already uses (the Python
+    // package sets it to torch's bundled copy: loading an older system libnccl first would
+    // break a later `import torch`).  A bare soname resolves to an already loaded copy.
+    void *h = nullptr;
+    if (const char *path = getenv("HALMA_NCCL_LIB")) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!h) return fail(HALMA_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
     g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
     g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
@@ -635,8 +640,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.group_size = potential_group_size(cfg.mode);
     L.rank = cfg.rank;
     L.n_ranks = cfg.n_ranks;
-    const int grid = P->ctx->sm_count * P->ctx->bps[cfg.mode];
-    L.target_items = 8 * grid * (kPotentialBlock / 32);
+    L.target_items = kNominalTickets;
     L.max_split = planes;
 
     PotParams &Q = P->pp;

@@ -327,7 +327,9 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
         }
         if (init) p.halo_buf[h] = 0;
         if (p.active[h]) {
-            groups += my_groups(p.cnt[h], p.group_size, p.rank, p.n_ranks);
+            // all ranks' groups: the j-split must depend on the problem only, so that a split
+            // run sums its partial potentials in the same grouping as a single-GPU run
+            groups += (p.cnt[h] + p.group_size - 1) / p.group_size;
             any = 1;
         }
     }

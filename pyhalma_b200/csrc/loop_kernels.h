@@ -10,6 +10,7 @@ namespace halma {
 constexpr int kChunk = 256;               // members per bookkeeping chunk
 constexpr int kMinSplitSources = 2048;    // never split a halo's sources into pieces below this
 constexpr int kMaxSplit = 8;              // planes of the partial-potential buffer
+constexpr int kNominalTickets = 32768;    // j-split aims at this many tickets per pass (machine-independent)
 
 struct LoopParams {
     // static description

@@ -1,7 +1,9 @@
 // Pipe-rate microbenchmark for the roofline denominator: how many
-// MUFU.RSQ, FFMA and packed FFMA2 instructions one SM retires per clock, and the SM clock
-// while doing so.  Every kernel runs one persistent block set per SM and times itself with
-// clock64(), so the result is in instructions per SM-clock and does not depend on DVFS.
+// MUFU.RSQ, FFMA and packed FFMA2 instructions the device retires per second, and the SM
+// clock while doing so (clock64 ticks against %globaltimer inside the kernel), from which
+// the per-SM-per-clock rates follow.  Rates come from CUDA-event time of a single resident
+// wave, so they do not depend on assumed occupancy.  See csrc/pipebench.cu for the full set
+// of instruction forms.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -11,42 +13,92 @@
 
 namespace halma {
 
-constexpr int kMbThreads = 512;
-constexpr int kMbIters = 4096;
+constexpr int kMbThreads = 256;
 constexpr int kMbIlp = 8;
+constexpr int kMbUnroll = 8;
+
+__device__ __forceinline__ unsigned long long mb_gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int OP>
-__global__ void __launch_bounds__(kMbThreads) k_pipe(float seed, long long *cycles, float *sink)
+__global__ void __launch_bounds__(kMbThreads) k_pipe(int iters, float seed, long long *ticks, unsigned long long *ns,
+                                                    float *sink)
 {
     float v[kMbIlp];
     uint64_t w[kMbIlp];
+    const float b = 1.0f + seed * 1e-3f, c = 0.25f + seed;
 #pragma unroll
     for (int k = 0; k < kMbIlp; ++k) {
         v[k] = seed + 0.001f * (threadIdx.x + k);
         w[k] = pack2(v[k], v[k] + 1.f);
     }
-    const uint64_t c2 = pack2(1.0001f, 0.9999f);
+    const uint64_t wb = pack2(b, b), wc = pack2(c, 2 * c);
     __syncthreads();
+    const unsigned long long g0 = mb_gtimer();
     const long long t0 = clock64();
 #pragma unroll 1
-    for (int it = 0; it < kMbIters; ++it) {
+    for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < kMbIlp; ++k) {
-            if (OP == 0) v[k] = rsqrt_ftz(v[k]);
-            if (OP == 1) v[k] = fmaf(v[k], 1.0001f, 0.5f);
-            if (OP == 2) w[k] = fma2(w[k], c2, c2);
+        for (int r = 0; r < kMbUnroll; ++r) {
+#pragma unroll
+            for (int k = 0; k < kMbIlp; ++k) {
+                if (OP == 0) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(v[k]));
+                if (OP == 1) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(v[k]) : "f"(b), "f"(c));
+                if (OP == 2) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(w[k]) : "l"(wb), "l"(wc));
+            }
         }
     }
     const long long t1 = clock64();
+    const unsigned long long g1 = mb_gtimer();
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < kMbIlp; ++k) {
-        float a, b;
-        unpack2(w[k], a, b);
-        acc += v[k] + a + b;
+        float lo, hi;
+        unpack2(w[k], lo, hi);
+        acc += v[k] + lo + hi;
     }
     if (acc == 123.456f) sink[0] = acc;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) {
+        ticks[blockIdx.x] = t1 - t0;
+        ns[blockIdx.x] = g1 - g0;
+    }
+}
+
+template <int OP>
+static int run_pipe(int sm, int iters, long long *d_ticks, unsigned long long *d_ns, float *d_sink, int max_blocks,
+                    double *gops, double *mhz)
+{
+    int bps = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pipe<OP>, kMbThreads, 0) != cudaSuccess || bps < 1)
+        return HALMA_ERR_CUDA;
+    const int blocks = std::min(sm * bps, max_blocks);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float ms = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        k_pipe<OP><<<blocks, kMbThreads>>>(iters, 1.5f, d_ticks, d_ns, d_sink);
+        cudaEventRecord(e1);
+        if (cudaDeviceSynchronize() != cudaSuccess) return HALMA_ERR_CUDA;
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    std::vector<long long> t(blocks);
+    std::vector<unsigned long long> n(blocks);
+    cudaMemcpy(t.data(), d_ticks, blocks * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(n.data(), d_ns, blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    std::sort(t.begin(), t.end());
+    std::sort(n.begin(), n.end());
+    *mhz = static_cast<double>(t[blocks / 2]) / static_cast<double>(n[blocks / 2]) * 1e3;
+    const double total = static_cast<double>(blocks) * kMbThreads * iters * kMbUnroll * kMbIlp;
+    *gops = total / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return HALMA_OK;
 }
 
 }  // namespace halma
@@ -59,46 +111,27 @@ extern "C" int halma_microbench(int device, double *out8)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HALMA_ERR_CUDA;
     const int sm = prop.multiProcessorCount;
-    const int blocks = sm * (2048 / kMbThreads);      // fill every SM with resident threads
-    long long *d_cyc = nullptr;
+    const int max_blocks = sm * 16;
+    long long *d_ticks = nullptr;
+    unsigned long long *d_ns = nullptr;
     float *d_sink = nullptr;
-    if (cudaMalloc(&d_cyc, blocks * sizeof(long long)) != cudaSuccess) return HALMA_ERR_CUDA;
-    if (cudaMalloc(&d_sink, 16) != cudaSuccess) return HALMA_ERR_CUDA;
-    std::vector<long long> cyc(blocks);
-    double rate[3] = {0, 0, 0}, mhz = 0.0;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    for (int op = 0; op < 3; ++op) {
-        for (int rep = 0; rep < 3; ++rep) {
-            cudaEventRecord(e0);
-            if (op == 0) k_pipe<0><<<blocks, kMbThreads>>>(1.5f, d_cyc, d_sink);
-            if (op == 1) k_pipe<1><<<blocks, kMbThreads>>>(1.5f, d_cyc, d_sink);
-            if (op == 2) k_pipe<2><<<blocks, kMbThreads>>>(1.5f, d_cyc, d_sink);
-            cudaEventRecord(e1);
-            if (cudaDeviceSynchronize() != cudaSuccess) return HALMA_ERR_CUDA;
-        }
-        cudaMemcpy(cyc.data(), d_cyc, blocks * sizeof(long long), cudaMemcpyDeviceToHost);
-        std::sort(cyc.begin(), cyc.end());
-        const double med = static_cast<double>(cyc[blocks / 2]);
-        // resident threads per SM * instructions per thread / cycles the SM took
-        const double per_thread = static_cast<double>(kMbIters) * kMbIlp;
-        rate[op] = 2048.0 * per_thread / med;
-        if (op == 0) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, e0, e1);
-            mhz = med / (ms * 1e-3) / 1e6;
-        }
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d_cyc);
+    if (cudaMalloc(&d_ticks, max_blocks * 8) != cudaSuccess || cudaMalloc(&d_ns, max_blocks * 8) != cudaSuccess ||
+        cudaMalloc(&d_sink, 16) != cudaSuccess)
+        return HALMA_ERR_CUDA;
+    double g[3] = {0, 0, 0}, mhz[3] = {0, 0, 0};
+    int rc = run_pipe<0>(sm, 4000, d_ticks, d_ns, d_sink, max_blocks, &g[0], &mhz[0]);
+    if (!rc) rc = run_pipe<1>(sm, 20000, d_ticks, d_ns, d_sink, max_blocks, &g[1], &mhz[1]);
+    if (!rc) rc = run_pipe<2>(sm, 10000, d_ticks, d_ns, d_sink, max_blocks, &g[2], &mhz[2]);
+    cudaFree(d_ticks);
+    cudaFree(d_ns);
     cudaFree(d_sink);
+    if (rc) return rc;
     memset(out8, 0, 8 * sizeof(double));
-    out8[0] = rate[0];
-    out8[1] = rate[1];
-    out8[2] = rate[2];
-    out8[3] = mhz;
+    for (int k = 0; k < 3; ++k) out8[k] = g[k] * 1e9 / (static_cast<double>(sm) * mhz[k] * 1e6);   // per clk per SM
+    out8[3] = mhz[0];
     out8[4] = sm;
+    out8[5] = g[0];      // absolute G instr/s
+    out8[6] = g[1];
+    out8[7] = g[2];
     return HALMA_OK;
 }

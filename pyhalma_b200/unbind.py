@@ -180,6 +180,7 @@ class UnbindPlan:
         _lib.check(self._L.halma_plan_set_vb(self._h, vb.ctypes.data))
 
     def join(self, unique_id: bytes):
+        _lib.ensure_nccl_path()
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _lib.check(self._L.halma_plan_join(self._h, buf))
 
@@ -210,6 +211,7 @@ class UnbindPlan:
 
 
 def nccl_unique_id() -> bytes:
+    _lib.ensure_nccl_path()
     buf = C.create_string_buffer(128)
     _lib.check(_lib.lib().halma_nccl_unique_id(buf))
     return buf.raw

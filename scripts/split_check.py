@@ -1,0 +1,47 @@
+"""Split mode (one halo shared by all ranks, one NCCL all-reduce per pass) against the
+single-GPU run of the same halo: results must be bit-identical.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/split_check.py
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from pyhalma_b200 import synth
+from pyhalma_b200.unbind import UnbindPlan, nccl_unique_id, unbind_halo
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000)):
+    c = synth.config1(n_star, n_gas, n_dm=500)
+    s, g, d = c.stars, c.gas, c.dm
+    uid = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    off = np.array([0, len(s)], np.int64)
+    eoff = [np.array([0, len(g)], np.int64), np.array([0, len(d)], np.int64)]
+    with UnbindPlan(off, eoff, mode=mode, n_pre=1, kappa=9.0, device=local, rank=rank, n_ranks=world) as plan:
+        plan.join(uid[0])
+        plan.upload_members(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass)
+        plan.upload_group(0, g.mass, g.x, g.y, g.z)
+        plan.upload_group(1, d.mass, d.x, d.y, d.z)
+        st = plan.run()
+        res = plan.download()
+    single = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, pre=[g.pos_mass()], post=[d.pos_mass()],
+                         kappa=9.0, mode=mode, device=local)
+    same = (np.array_equal(res.mask.astype(bool), single.mask)
+            and np.array_equal(res.be32.view(np.uint32), single.be32.view(np.uint32))
+            and np.array_equal(res.energy, single.energy) and res.halos[0].n_iter == single.n_iter
+            and res.halos[0].vb == single.vb and res.halos[0].pairs == single.pairs)
+    flag = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("split %s: n=%d passes=%d bound=%d identical_on_all_ranks=%s  (split %.2f ms, single %.2f ms)" % (
+            mode, len(s), res.halos[0].n_iter, res.halos[0].n_bound, bool(flag.item()), st.total_ms,
+            single.stats.total_ms), flush=True)
+    ok = ok and bool(flag.item())
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
