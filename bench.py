@@ -187,7 +187,8 @@ def cpu_sample(jobs, n_targets: int):
     from oracle import oracle as O
     f32 = np.float32
     pairs, secs = 0, 0.0
-    threads = O.max_threads()
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     for job in jobs:
         off = job["offsets"]
         h = int(np.argmax(np.diff(off)))
@@ -258,7 +259,7 @@ def e2e_step(jobs_pinned, mode, device, rank=0, world=1):
         finally:
             plan.close()
         n = len(job["members"][0])
-        pairs += st.pairs
+        pairs += st.pairs // world if (job["split"] and world > 1) else st.pairs
         h2d += 7 * 8 * n + sum(4 * 8 * len(g[1]) for g in job["groups"])
         d2h += n * (1 + 4 + 8 + 4) + 80 * (len(job["offsets"]) - 1)
     return pairs, h2d, d2h
@@ -305,10 +306,11 @@ def run_gpu(args, rank, local_rank, world):
     busy_windows = []
     for _ in range(args.steps):
         tb = time.perf_counter()
-        for st in step():
+        for st, job in zip(step(), jobs):
             dev_ms += st.total_ms
             pot_ms += st.potential_ms
-            pairs += st.pairs
+            # in split mode every rank's counter covers the whole halo: count it once
+            pairs += st.pairs // world if (job["split"] and world > 1) else st.pairs
             launches += st.launches
             pot_launches += st.potential_launches
             passes += st.passes
@@ -351,6 +353,7 @@ def run_gpu(args, rank, local_rank, world):
             pass
         value = pairs_all / (dev_ms_max * 1e-3) / 1e9
         # roofline of the dominant kernel (rank 0's launches)
+        # rank 0's share of the work (already divided in split mode) over rank 0's kernel time
         pot_rate = pairs / (pot_ms * 1e-3) / 1e9
         sm_mhz = clocks.get("sm_mhz") or mb["sm_clock_mhz"]
         peak = mb["rsq_per_clk_sm"] * mb["sm_count"] * sm_mhz * 1e6 / 1e9
@@ -372,10 +375,13 @@ def run_gpu(args, rank, local_rank, world):
             "traffic": None,
             "microbench": mb,
         }
-        cp, cs, threads = cpu_sample(jobs, args.cpu_targets)
-        cpu = {"value": cp / cs / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "first pass, first %d targets of each job x all sources (%.1f s of CPU work); "
-                         "oracle/ f32seq, OpenMP" % (args.cpu_targets, cs)}
+        if world == 1:
+            cp, cs, threads = cpu_sample(jobs, args.cpu_targets)
+            cpu = {"value": cp / cs / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "first pass, first %d targets of each job x all sources (%.1f s of CPU work); "
+                             "oracle/ f32seq, OpenMP" % (args.cpu_targets, cs)}
+        else:
+            cpu = None          # reported at N = 1 only
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,

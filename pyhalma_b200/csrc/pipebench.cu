@@ -17,12 +17,15 @@ constexpr int kUnroll = 8;       // kIlp * kUnroll instructions per loop trip
 __device__ __forceinline__ uint64_t pk(float a, float b) { uint64_t r; asm("mov.b64 %0,{%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ uint64_t gtimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-enum Op { RSQ, FFMA_REG, FFMA_IMM, FADD_REG, FADD2_REG, FADD2_BCAST, FMUL2, FFMA2, FMNMX3, FSETP_SEL, BODY_PACKED, BODY_SCALAR, N_OPS };
+enum Op { RSQ, FFMA_REG, FFMA_IMM, FADD_REG, FADD2_REG, FADD2_BCAST, FMUL2, FFMA2, FMNMX3, FSETP_SEL, BODY_PACKED, BODY_SCALAR,
+          MIX_FADD2_FMNMX3, MIX_FADD2_RSQ, MIX_FADD2_FFMA, MIX_FFMA_FMNMX3, MIX_FFMA_RSQ, MIX_FADD_FADD2, FSETP_ONLY, BODY_NOPRED, N_OPS };
 static const char *kNames[N_OPS] = {"mufu_rsq", "ffma_reg", "ffma_imm", "fadd_reg", "fadd2_reg", "fadd2_bcast", "fmul2",
-                                    "ffma2", "fmnmx3", "fsetp_ffma_pred", "body_packed(2 inter)", "body_scalar(1 inter)"};
+                                    "ffma2", "fmnmx3", "fsetp_ffma_pred", "body_packed(2 inter)", "body_scalar(1 inter)",
+                                    "mix fadd2+fmnmx3", "mix fadd2+rsq", "mix fadd2+ffma", "mix ffma+fmnmx3", "mix ffma+rsq",
+                                    "mix fadd+fadd2", "fsetp+sel", "body_nopred(2 inter)"};
 // thread-instructions issued per "op" (for BODY_*: issue slots of one body)
-static const int kSlots[N_OPS] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 14, 11};
-static const int kInter[N_OPS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 1};
+static const int kSlots[N_OPS] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 14, 11, 2, 2, 2, 2, 2, 2, 2, 9};
+static const int kInter[N_OPS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 2};
 
 template <int OP>
 __global__ void __launch_bounds__(kThreads) k(int iters, float seed, float4 *out, long long *ticks, unsigned long long *ns)
@@ -74,7 +77,32 @@ __global__ void __launch_bounds__(kThreads) k(int iters, float seed, float4 *out
                     asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(r1));
                     asm volatile("{.reg .pred p; setp.gt.f32 p, %1, 0f00000000; @p fma.rn.f32 %0, %2, %3, %0;}" : "+f"(v[k]) : "f"(t0_), "f"(u[k]), "f"(i0));
                     asm volatile("{.reg .pred p; setp.gt.f32 p, %1, 0f00000000; @p fma.rn.f32 %0, %2, %3, %0;}" : "+f"(v[k]) : "f"(t1_), "f"(u[k]), "f"(i1));
+                    w[k] = dx;      // loop-carried: nothing is invariant
                 }
+                if (OP == BODY_NOPRED) {
+                    // two interactions without the exclusion predicate and with a packed accumulate
+                    uint64_t dx, dy, dz, r2, inv;
+                    float r0, r1, i0, i1;
+                    asm volatile("{.reg .b64 t; mov.b64 t,{%1,%1}; sub.rn.f32x2 %0, %2, t;}" : "=l"(dx) : "f"(a), "l"(w[k]));
+                    asm volatile("{.reg .b64 t; mov.b64 t,{%1,%1}; sub.rn.f32x2 %0, %2, t;}" : "=l"(dy) : "f"(b), "l"(w[(k + 1) % kIlp]));
+                    asm volatile("{.reg .b64 t; mov.b64 t,{%1,%1}; sub.rn.f32x2 %0, %2, t;}" : "=l"(dz) : "f"(c), "l"(w[(k + 2) % kIlp]));
+                    asm volatile("mul.rn.f32x2 %0, %1, %1;" : "=l"(r2) : "l"(dy));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(r2) : "l"(dx));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(r2) : "l"(dz));
+                    asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r2));
+                    asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(r0));
+                    asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(r1));
+                    asm volatile("mov.b64 %0, {%1,%2};" : "=l"(inv) : "f"(i0), "f"(i1));
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(w[(k + 3) % kIlp]) : "l"(wb), "l"(inv));
+                    w[k] = dx;
+                }
+                if (OP == MIX_FADD2_FMNMX3) { asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[k]) : "l"(wc)); asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(v[k]) : "f"(b), "f"(u[k])); }
+                if (OP == MIX_FADD2_RSQ) { asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[k]) : "l"(wc)); asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(v[k])); }
+                if (OP == MIX_FADD2_FFMA) { asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[k]) : "l"(wc)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(v[k]) : "f"(b), "f"(c)); }
+                if (OP == MIX_FFMA_FMNMX3) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(u[k]) : "f"(b), "f"(c)); asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(v[k]) : "f"(b), "f"(c)); }
+                if (OP == MIX_FFMA_RSQ) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(u[k]) : "f"(b), "f"(c)); asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(v[k])); }
+                if (OP == MIX_FADD_FADD2) { asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(v[k]) : "f"(c)); asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[k]) : "l"(wc)); }
+                if (OP == FSETP_ONLY) { asm volatile("{.reg .pred p; setp.gt.f32 p, %0, %1; selp.f32 %0, %2, %0, p;}" : "+f"(v[k]) : "f"(u[k]), "f"(b)); }
                 if (OP == BODY_SCALAR) {
                     float dx, dy, dz, r2, t_, i_;
                     float lo, hi;
@@ -88,6 +116,8 @@ __global__ void __launch_bounds__(kThreads) k(int iters, float seed, float4 *out
                     asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(t_) : "f"(fabsf(dx)), "f"(fabsf(dy)), "f"(fabsf(dz)));
                     asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(i_) : "f"(r2));
                     asm volatile("{.reg .pred p; setp.gt.f32 p, %1, 0f00000000; @p fma.rn.f32 %0, %2, %3, %0;}" : "+f"(v[k]) : "f"(t_), "f"(b), "f"(i_));
+                    w[k] = pk(dx, dy);
+                    u[k] = dz;
                 }
             }
         }
@@ -154,6 +184,9 @@ int main(int argc, char **argv)
     const int sm = p.multiProcessorCount;
     run<RSQ>(sm, iters); run<FFMA_REG>(sm, iters); run<FFMA_IMM>(sm, iters); run<FADD_REG>(sm, iters);
     run<FADD2_REG>(sm, iters); run<FADD2_BCAST>(sm, iters); run<FMUL2>(sm, iters); run<FFMA2>(sm, iters);
-    run<FMNMX3>(sm, iters); run<FSETP_SEL>(sm, iters); run<BODY_PACKED>(sm, iters / 4); run<BODY_SCALAR>(sm, iters / 4);
+    run<FMNMX3>(sm, iters); run<FSETP_SEL>(sm, iters); run<FSETP_ONLY>(sm, iters);
+    run<MIX_FADD2_FMNMX3>(sm, iters); run<MIX_FADD2_RSQ>(sm, iters); run<MIX_FADD2_FFMA>(sm, iters); run<MIX_FFMA_FMNMX3>(sm, iters);
+    run<MIX_FFMA_RSQ>(sm, iters); run<MIX_FADD_FADD2>(sm, iters);
+    run<BODY_PACKED>(sm, iters / 4); run<BODY_SCALAR>(sm, iters / 4); run<BODY_NOPRED>(sm, iters / 4);
     return 0;
 }
