@@ -81,6 +81,10 @@ static int get_ctx(int device, DeviceCtx **out)
         CU_TRY(potential_configure(HALMA_MODE_FAST, &c.bps[HALMA_MODE_FAST]));
         CU_TRY(potential_configure(HALMA_MODE_EXACT, &c.bps[HALMA_MODE_EXACT]));
         CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CU_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;      // keep freed blocks in the pool for the next plan
+        CU_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         c.ready = true;
     }
     *out = &c;
@@ -137,14 +141,20 @@ extern "C" int halma_host_free(void *ptr)
 static inline int64_t up4(int64_t n) { return (n + 3) & ~int64_t(3); }
 static inline size_t up256(size_t n) { return (n + 255) & ~size_t(255); }
 
+// Device buffer from the device's default memory pool (stream-ordered).  The pool's release
+// threshold is raised in get_ctx(), so memory freed by one plan is reused by the next
+// without going back to the driver: one-shot calls do not pay cudaMalloc/cudaFree.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+
 template <class T>
 struct DBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t s = nullptr;
     DBuf() = default;
     DBuf(const DBuf &) = delete;
     DBuf &operator=(const DBuf &) = delete;
-    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n)
+    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n), s(o.s)
     {
         o.p = nullptr;
         o.n = 0;
@@ -153,11 +163,12 @@ struct DBuf {
     {
         release();
         n = count;
-        return cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+        s = g_alloc_stream;
+        return cudaMallocAsync(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T), s);
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, s);
         p = nullptr;
         n = 0;
     }
@@ -440,8 +451,19 @@ struct halma_plan {
     LoopParams lp;
     PotParams pp;
 
+    void free_buffers()
+    {
+        d_halo.release(); d_chunk_halo.release(); d_chunk_p0.release(); d_order.release();
+        d_ext_off.clear();
+        d_in.release(); d_ext.release(); d_stage.release(); d_vb_user.release(); d_work.release();
+        d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_cint.release();
+        d_csum.release(); d_flag.release(); d_mask.release(); d_be.release(); d_E.release();
+        d_idx.release(); d_phi.release(); d_st.release();
+    }
     ~halma_plan()
     {
+        free_buffers();                       // stream-ordered frees, before the stream goes away
+        if (stream) cudaStreamSynchronize(stream);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         for (auto e : ev) cudaEventDestroy(e);
         if (ev_start) cudaEventDestroy(ev_start);
@@ -455,6 +477,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
 {
     const halma_unbind_config &cfg = P->cfg;
     const int64_t nh = P->n_halo;
+    g_alloc_stream = P->stream;
     P->offsets.assign(offsets, offsets + nh + 1);
     if (P->offsets[0] != 0) return fail(HALMA_ERR_INVALID, "offsets[0] must be 0");
     for (int64_t h = 0; h < nh; ++h)
