@@ -13,6 +13,7 @@
 
 #include "loop_kernels.h"
 #include "potential.h"
+#include "sortprep.h"
 
 using namespace halma;
 
@@ -448,6 +449,18 @@ struct halma_plan {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     void *comm = nullptr;                 // ncclComm_t (split mode)
     bool ran = false;
+    // predicate-free FAST path: sorted source copies (sortprep.cu)
+    bool np = false, sorted_dirty = true;
+    int64_t n_spad = 0, n_valid = 0, n_tot = 0;
+    int max_ext = 0;
+    size_t sort_temp_bytes = 0;
+    DBuf<int32_t> d_src_halo, d_sslot, d_stgt, d_sinv, d_redo, d_nsel;
+    DBuf<uint64_t> d_keys;
+    DBuf<uint32_t> d_ids, d_skey;
+    DBuf<uint8_t> d_ismem, d_sorttemp;
+    DBuf<float> d_sf;
+    DBuf<double> d_corr;
+    SortedAxisMut sax[3];
     LoopParams lp;
     PotParams pp;
 
@@ -459,6 +472,9 @@ struct halma_plan {
         d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_cint.release();
         d_csum.release(); d_flag.release(); d_mask.release(); d_be.release(); d_E.release();
         d_idx.release(); d_phi.release(); d_st.release();
+        d_src_halo.release(); d_sslot.release(); d_stgt.release(); d_sinv.release(); d_redo.release();
+        d_nsel.release(); d_keys.release(); d_ids.release(); d_skey.release(); d_ismem.release();
+        d_sorttemp.release(); d_sf.release(); d_corr.release();
     }
     ~halma_plan()
     {
@@ -512,7 +528,11 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
 
     std::vector<HaloDesc> halo(nh);
     std::vector<int32_t> chunk_halo, chunk_p0;
-    int64_t poff = 0, eoff = 0;
+    int64_t poff = 0, eoff = 0, soff = 0, doff = 0;
+    {
+        const char *e = getenv("HALMA_NP");
+        P->np = cfg.mode == HALMA_MODE_FAST && cfg.n_ranks == 1 && !(e && atoi(e) == 0);
+    }
     for (int64_t h = 0; h < nh; ++h) {
         HaloDesc &d = halo[h];
         memset(&d, 0, sizeof d);
@@ -541,11 +561,20 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
         }
         if (next > 0x7ffffff0ll) return fail(HALMA_ERR_TOO_LARGE, "too many external sources for one halo");
         d.n_ext = static_cast<int32_t>(next);
+        d.sbegin = soff;
+        d.dbegin = doff;
+        soff += up4(n0 + next);
+        doff += n0 + next;
+        P->max_ext = std::max<int>(P->max_ext, static_cast<int>(std::min<int64_t>(next, 0x7fffffff)));
         poff += up4(n0);
     }
+    P->n_spad = soff + 16;
+    P->n_valid = doff;
     P->n_pad = poff + 16;
     P->n_ext_pad = eoff + 16;
     P->n_chunks = static_cast<int>(chunk_halo.size());
+    P->n_tot = P->n_pad + P->n_ext_pad;
+    if (P->n_tot > 0x7ffffff0ll || P->n_spad > 0x7ffffff0ll || P->n_user == 0) P->np = false;
 
     std::vector<int32_t> order(nh);
     std::iota(order.begin(), order.end(), 0);
@@ -593,6 +622,39 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     const int planes = cfg.mode == HALMA_MODE_FAST ? kMaxSplit : 1;
     CU_TRY(P->d_phi.alloc(planes * NP));
     CU_TRY(P->d_st.alloc(1));
+    CU_TRY(P->d_redo.alloc(nh));
+    if (P->np) {
+        const size_t NT = static_cast<size_t>(P->n_tot), NS = static_cast<size_t>(P->n_spad);
+        CU_TRY(P->d_src_halo.alloc(NT));
+        CU_TRY(P->d_keys.alloc(2 * NT));
+        CU_TRY(P->d_ids.alloc(2 * NT));
+        CU_TRY(P->d_ismem.alloc(NS));
+        CU_TRY(P->d_nsel.alloc(4));
+        P->sort_temp_bytes = sorted_temp_bytes(P->n_tot, P->n_spad);
+        CU_TRY(P->d_sorttemp.alloc(P->sort_temp_bytes));
+        CU_TRY(P->d_sf.alloc(15 * NS));
+        CU_TRY(P->d_skey.alloc(3 * NS));
+        CU_TRY(P->d_sslot.alloc(3 * NS));
+        CU_TRY(P->d_stgt.alloc(3 * std::max<size_t>(NU, 1)));
+        CU_TRY(P->d_sinv.alloc(3 * NP));
+        CU_TRY(P->d_corr.alloc(3 * NP));
+        CU_TRY(cudaMemsetAsync(P->d_corr.p, 0, 3 * NP * sizeof(double), s));
+        CU_TRY(cudaMemsetAsync(P->d_sinv.p, 0, 3 * NP * sizeof(int32_t), s));
+        for (int a = 0; a < 3; ++a) {
+            SortedAxisMut &A = P->sax[a];
+            float *f = P->d_sf.p + static_cast<size_t>(a) * 5 * NS;
+            A.x = f;
+            A.y = f + NS;
+            A.z = f + 2 * NS;
+            A.m = f + 3 * NS;
+            A.m0 = f + 4 * NS;
+            A.key = P->d_skey.p + a * NS;
+            A.slot = P->d_sslot.p + a * NS;
+            A.tgt = P->d_stgt.p + a * std::max<size_t>(NU, 1);
+            A.inv = P->d_sinv.p + a * NP;
+            A.corr = P->d_corr.p + a * NP;
+        }
+    }
     CU_TRY(cudaMemsetAsync(P->d_work.p, 0, 8 * NP * sizeof(float), s));
     CU_TRY(cudaMemsetAsync(P->d_ext.p, 0, 4 * static_cast<size_t>(P->n_ext_pad) * sizeof(float), s));
     CU_TRY(cudaMemsetAsync(P->d_vb_user.p, 0, 3 * nh * sizeof(double), s));
@@ -665,6 +727,12 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.n_ranks = cfg.n_ranks;
     L.target_items = kNominalTickets;
     L.max_split = planes;
+    L.halo_redo = P->d_redo.p;
+    L.np_enabled = P->np ? 1 : 0;
+    for (int a = 0; a < 3 && P->np; ++a) {
+        const SortedAxisMut &A = P->sax[a];
+        L.ax[a] = SortedAxis{A.x, A.y, A.z, A.m, A.key, A.slot, A.tgt, A.inv, A.corr};
+    }
 
     PotParams &Q = P->pp;
     memset(&Q, 0, sizeof Q);
@@ -688,7 +756,55 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     Q.tgt_members = 1;
     Q.rank = cfg.rank;
     Q.n_ranks = cfg.n_ranks;
+    Q.halo_redo = P->d_redo.p;
+    Q.np_enabled = P->np ? 1 : 0;
+    Q.redo_only = 0;
+    for (int a = 0; a < 3 && P->np; ++a) {
+        Q.ax[a] = L.ax[a];
+        Q.src[3 + a] = F32Set{P->sax[a].x, P->sax[a].y, P->sax[a].z, P->sax[a].m};
+    }
     CU_TRY(cudaStreamSynchronize(s));
+    return HALMA_OK;
+}
+
+// Sorted source copies of the predicate-free path: (re)built after an upload, masses
+// restored before every run (the loop zeroes the masses of removed members).
+static int plan_prepare_sorted(halma_plan *P)
+{
+    if (!P->np) return HALMA_OK;
+    cudaStream_t s = P->stream;
+    const size_t NS = static_cast<size_t>(P->n_spad), NT = static_cast<size_t>(P->n_tot);
+    if (P->sorted_dirty) {
+        CU_TRY(sorted_fill_src_halo(P->d_halo.p, static_cast<int>(P->n_halo), P->d_chunk_halo.p, P->d_chunk_p0.p,
+                                    P->n_chunks, P->max_ext, P->n_pad, P->n_tot, P->d_src_halo.p, s));
+        const size_t NE = static_cast<size_t>(P->n_ext_pad);
+        SortedBuild b;
+        b.halo = P->d_halo.p;
+        b.src_halo = P->d_src_halo.p;
+        b.mem = F32Set{P->lp.wx[0], P->lp.wy[0], P->lp.wz[0], P->lp.wm[0]};
+        b.ext = F32Set{P->d_ext.p, P->d_ext.p + NE, P->d_ext.p + 2 * NE, P->d_ext.p + 3 * NE};
+        b.n_pad = P->n_pad;
+        b.n_tot = P->n_tot;
+        b.n_valid = P->n_valid;
+        b.n_spad = P->n_spad;
+        b.n_halo = static_cast<int32_t>(P->n_halo);
+        b.keys_in = P->d_keys.p;
+        b.keys_out = P->d_keys.p + NT;
+        b.ids_in = P->d_ids.p;
+        b.ids_out = P->d_ids.p + NT;
+        b.is_member = P->d_ismem.p;
+        b.n_selected = P->d_nsel.p;
+        b.temp = P->d_sorttemp.p;
+        b.temp_bytes = P->sort_temp_bytes;
+        for (int a = 0; a < 3; ++a) {
+            b.out = &P->sax[a];
+            CU_TRY(sorted_build_axis(b, a, s));
+        }
+        P->sorted_dirty = false;
+    } else {
+        for (int a = 0; a < 3; ++a)
+            CU_TRY(cudaMemcpyAsync(P->sax[a].m, P->sax[a].m0, NS * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
     return HALMA_OK;
 }
 
@@ -746,6 +862,7 @@ extern "C" int halma_plan_upload_members(halma_plan *P, const double *x, const d
         if (NU) CU_TRY(cudaMemcpyAsync(P->d_in.p + k * NU, src[k], NU * 8, cudaMemcpyHostToDevice, P->stream));
     }
     P->members_up = true;
+    P->sorted_dirty = true;
     return HALMA_OK;
 }
 
@@ -769,6 +886,7 @@ extern "C" int halma_plan_upload_group(halma_plan *P, int group, const double *m
                                  P->d_stage.p + 3 * n, e + 3 * NE, e, e + NE, e + 2 * NE, P->stream));
     }
     P->group_up[group] = true;
+    P->sorted_dirty = true;
     return HALMA_OK;
 }
 
@@ -801,6 +919,12 @@ static int enqueue_pass(halma_plan *P, int pass)
     const int grid = sm * P->ctx->bps[P->cfg.mode];
     CU_TRY(cudaEventRecord(P->ev[3 * pass], s));
     CU_TRY(potential_launch(P->pp, P->cfg.mode, grid, s));
+    if (P->np) {
+        // haloes whose predicate-free sums came out non-finite are recomputed with the predicate
+        PotParams redo = P->pp;
+        redo.redo_only = 1;
+        CU_TRY(potential_launch(redo, P->cfg.mode, grid, s));
+    }
     CU_TRY(cudaEventRecord(P->ev[3 * pass + 1], s));
     if (P->cfg.n_ranks > 1) {
         CU_TRY(launch_fold_partials(P->lp, sm, s));
@@ -843,6 +967,7 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         CU_TRY(cudaMemcpyAsync(P->lp.hvb, P->d_vb_user.p, 3 * nh * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if (nh > 0) {
         CU_TRY(launch_pack_members(P->lp, sm, s));
+        if (int rc = plan_prepare_sorted(P)) return rc;
         CU_TRY(launch_halo_decide(P->lp, 1, sm, s));
         CU_TRY(launch_schedule(P->lp, 1, s));
         launches += 3;
@@ -865,7 +990,7 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
             ++passes;
             if (!still) done = true;
         }
-        launches += queued * (5 + (P->cfg.n_ranks > 1 ? 2 : 0));
+        launches += queued * (5 + (P->cfg.n_ranks > 1 ? 2 : 0) + (P->np ? 1 : 0));
         pot_launches = queued;
         CU_TRY(launch_finalize(P->lp, sm, s));
         ++launches;

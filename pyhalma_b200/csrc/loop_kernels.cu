@@ -164,6 +164,11 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
             const int S = p.nsplit[h];
             double phi = p.phi_part[i];
             for (int k = 1; k < S; ++k) phi += p.phi_part[static_cast<int64_t>(k) * p.n_pad + i];
+            if (p.np_enabled && !p.halo_redo[h]) {
+                // predicate-free path: take out the pairs that share a coordinate (potential.cu)
+                const int64_t slot = hd.poff + (g - hd.uoff);
+                phi -= (p.ax[0].corr[slot] + p.ax[1].corr[slot]) + p.ax[2].corr[slot];
+            }
             const float be = __double2float_rn(phi);
             // halo_properties.py:342-351 / halo_gas.py:456-465: float32 chain, two roundings
             float pe = -be;
@@ -292,6 +297,12 @@ __global__ void __launch_bounds__(kCh) k_compact(const LoopParams p)
         __syncthreads();
         int base = 0;
         for (int w = 0; w < warp; ++w) base += woff[w];
+        if (p.np_enabled && q < n && !f) {
+            // a removed member stops being a source of the correction tickets
+            const int64_t slot = hd.poff + (p.widx[par][i] - hd.uoff);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p.ax[a].m[p.ax[a].inv[slot]] = 0.f;
+        }
         if (f) {
             const int64_t d = hd.poff + p.chunk_off[c] + base + rank_in_warp;
             p.wx[nxt][d] = p.wx[par][i];
@@ -326,6 +337,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
             for (int k = 0; k < 3; ++k) p.hvb[3 * h + k] = p.hvb_next[3 * h + k];
         }
         if (init) p.halo_buf[h] = 0;
+        if (p.np_enabled) p.halo_redo[h] = 0;
         if (p.active[h]) {
             // all ranks' groups: the j-split must depend on the problem only, so that a split
             // run sums its partial potentials in the same grouping as a single-GPU run
@@ -367,6 +379,8 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
                 p.nsplit[h] = S;
                 max_split = max(max_split, S);
                 items = my_groups(n, p.group_size, p.rank, p.n_ranks) * S;
+                // correction tickets: three axes x blocks of the (static) sorted member list
+                if (p.np_enabled) items += 3 * ((p.halo[h].n0 + p.group_size - 1) / p.group_size);
             }
         }
         // inclusive warp scan
@@ -400,6 +414,8 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
         st->n_items = s_carry;
         st->any_active = s_any;
         st->counter = 0u;
+        st->counter_redo = 0u;
+        st->redo_any = 0;
         if (init) {
             st->parity = 0;
             st->pass = 0;

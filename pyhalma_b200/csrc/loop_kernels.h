@@ -40,6 +40,10 @@ struct LoopParams {
     LoopState *st;
     float G32, kappa32;
     int32_t vb_fixed, max_iter, mode, group_size, rank, n_ranks, target_items, max_split;
+    // predicate-free FAST path (potential.cu): sorted copies + per-halo fallback flags
+    SortedAxis ax[3];
+    int32_t *halo_redo;
+    int32_t np_enabled;
 };
 
 cudaError_t launch_pack_members(const LoopParams &p, int sm_count, cudaStream_t s);

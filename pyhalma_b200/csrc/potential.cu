@@ -4,21 +4,36 @@
 //   be(i) = sum_j [x_j != x_i && y_j != y_i && z_j != z_i]  m_j / sqrt(dx^2 + dy^2 + dz^2)
 //
 // Work decomposition: a persistent grid; every WARP takes tickets from a device counter.
-// A ticket is (halo, target group, j-split): kTargets*32 targets held in registers against
+// A main ticket is (halo, target group, j-split): 32*T targets held in registers against
 // 1/S of every source segment of that halo.  Sources are streamed through a warp-private
 // ring of shared-memory tiles filled by 1-D TMA bulk copies (cp.async.bulk, UBLKCP) that
 // complete on a per-stage mbarrier, so no block-wide barrier is ever taken and warps of
 // one block can work on different haloes.
 //
-// FAST kernel, per pair of sources (j, j+1) and one target (7 issue slots per interaction):
-//   3 FADD2 (dx,dy,dz) + FMUL2 + 2 FFMA2 (r^2) + 2 FMNMX3 + 2 FSETP (exclusion predicate:
-//   min(|dx|,|dy|,|dz|) > 0  <=>  all three coordinates differ) + 2 MUFU.RSQ + 2 predicated
-//   FFMA (acc += m * rsqrt).  float32 partial sums over <= 32 sources are flushed into a
-//   float64 accumulator.  Bound: MUFU, 16 interactions / clk / SM.
+// Three arithmetic paths share that machinery:
 //
-// EXACT kernel: one target per thread, sources strictly in ascending order, IEEE sqrt and
-// divide, the reference's != predicate, float32 accumulator: bit-identical to the reference
-// arithmetic (see oracle/halma_oracle.c for the contraction of r^2).
+// EXACT  one target per thread, sources strictly in ascending order, IEEE sqrt and divide,
+//        the reference's != predicate, float32 accumulator: bit-identical to the reference
+//        (see oracle/halma_oracle.c for the contraction of r^2).
+//
+// FAST, predicated ("PRED")  per pair of sources and one target: 3 FADD2 + FMUL2 + 2 FFMA2,
+//        2 FMNMX3 + 2 FSETP (min(|dx|,|dy|,|dz|) > 0 <=> all three coordinates differ),
+//        2 MUFU.RSQ, 2 predicated FFMA.  Packed f32x2 instructions hold the dispatch port
+//        for two cycles, so this body is dispatch-bound at ~21 cycles per source pair
+//        against MUFU's 16 (profiles/ncu_fast_r01.md).
+//
+// FAST, predicate-free ("NP", default for plans)  the two predicate instructions per
+//        interaction leave the hot loop: main tickets sum over ALL sources with a packed
+//        accumulate (18 cycles per pair); only the tile that contains the group's own
+//        members keeps an r^2 > 0 guard (self pairs).  The pairs the reference excludes are
+//        then subtracted exactly by CORRECTION tickets: for each axis the halo's sources are
+//        kept sorted by that coordinate's bit pattern (sortprep.cu), so the sources that can
+//        share a coordinate with 128 consecutive members of the sorted order form one
+//        contiguous range; the correction body counts a pair iff it shares this axis and no
+//        lower axis (each excluded pair exactly once).  A sum that comes out non-finite
+//        (zero separation outside the own tile: exact duplicates) flags the halo, which is
+//        then recomputed by the predicated kernel, so correctness never rests on the fast
+//        path.  float32 partial sums over <= 32 sources are flushed into float64.
 #include <cstdlib>
 
 #include "halma_common.cuh"
@@ -34,8 +49,9 @@ constexpr int kWarpsPerBlock = kPotentialBlock / 32;
 constexpr int kSmemBytes = kWarpsPerBlock * kStages * (kStageFloats * 4 + 8);
 
 // ---------------------------------------------------------------------------------------
-// Cursor over the source tiles of one ticket: piece `s` of `S` of every segment, in
-// segment order.  Uniform across the warp.
+// Cursor over the source tiles of one ticket.  Main tickets: piece `s` of `S` of every
+// segment of the halo, in segment order.  Correction tickets: one explicit range of a
+// sorted copy.  Uniform across the warp.
 // ---------------------------------------------------------------------------------------
 struct TileCursor {
     const HaloDesc *hd;
@@ -73,6 +89,21 @@ struct TileCursor {
         parity = parity_;
         seek();
     }
+    __device__ __forceinline__ void init_range(int set_, int64_t begin, int count)
+    {
+        hd = nullptr;
+        nseg = 1;
+        k = count > 0 ? 0 : 1;
+        S = 1;
+        s = 0;
+        n_members = 0;
+        parity = 0;
+        base = begin;
+        set = set_;
+        pos = 0;
+        end = count;
+        flags = 0;
+    }
     __device__ __forceinline__ bool valid() const { return k < nseg; }
     __device__ __forceinline__ int len() const { return min(kTileJ, end - pos); }
     __device__ __forceinline__ void next()
@@ -80,14 +111,14 @@ struct TileCursor {
         pos += kTileJ;
         if (pos >= end) {
             ++k;
-            seek();
+            if (hd) seek();
         }
     }
 };
 
 // Fill one stage with the cursor's tile.  Whole quads come by TMA; the last 1..3 sources of
 // a segment are fetched with plain loads (never reading past the array) and the quad is
-// padded with (inf, inf, inf, m = 0), which contributes exactly zero in both kernels.
+// padded with (inf, inf, inf, m = 0), which contributes exactly zero in every body.
 __device__ __forceinline__ void issue_tile(const PotParams &p, const TileCursor &c, float *stage, uint64_t *bar,
                                            int lane)
 {
@@ -124,12 +155,16 @@ __device__ __forceinline__ void issue_tile(const PotParams &p, const TileCursor 
 }
 
 // ---------------------------------------------------------------------------------------
-// Ticket decoding shared by both kernels.
+// Tickets
 // ---------------------------------------------------------------------------------------
 struct Ticket {
     int h, group, s, S, n_tgt;
+    int corr_axis;      // -1: main ticket; 0..2: correction ticket of that axis, `group` = block
 };
 
+// Ticket layout of a halo (must match loop_kernels.cu::k_schedule):
+//   [0, mine * S)                    main tickets, s-major
+//   [mine * S, mine * S + 3 * nblk)  correction tickets (NP path), axis-major
 template <int kGroup>
 __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Ticket &t)
 {
@@ -142,42 +177,77 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
         else
             hi = mid;
     }
-    const int local = item - p.item_base[lo];
+    int local = item - p.item_base[lo];
     t.h = p.order[lo];
     t.n_tgt = p.cnt ? p.cnt[t.h] : p.halo[t.h].n0;
     t.S = p.nsplit[t.h];
+    t.corr_axis = -1;
     const int groups = (t.n_tgt + kGroup - 1) / kGroup;
     const int mine = (groups - p.rank + p.n_ranks - 1) / p.n_ranks;
-    if (mine <= 0) return false;
-    t.s = local / mine;
-    t.group = (local % mine) * p.n_ranks + p.rank;
+    const int n_main = mine * t.S;
+    if (local < n_main) {
+        t.s = local / mine;
+        t.group = (local % mine) * p.n_ranks + p.rank;
+        return true;
+    }
+    if (!p.np_enabled) return false;
+    local -= n_main;
+    const int nblk = (p.halo[t.h].n0 + kGroup - 1) / kGroup;
+    if (nblk <= 0 || local >= 3 * nblk) return false;
+    t.corr_axis = local / nblk;
+    t.group = local % nblk;
+    t.s = 0;
     return true;
 }
 
 // ---------------------------------------------------------------------------------------
-// FAST kernel
+// FAST bodies
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void pair_fast(uint64_t X, uint64_t Y, uint64_t Z, float m0, float m1, float xi, float yi,
-                                          float zi, float &acc)
+enum Body { kPred = 0, kNp = 1, kGuard = 2, kCorrX = 3, kCorrY = 4, kCorrZ = 5 };
+
+template <int BODY>
+__device__ __forceinline__ void pair_body(uint64_t X, uint64_t Y, uint64_t Z, float m0, float m1, float xi, float yi,
+                                          float zi, float &acc, uint64_t &acc2)
 {
     const uint64_t dx = sub2(X, pack2(xi, xi));
     const uint64_t dy = sub2(Y, pack2(yi, yi));
     const uint64_t dz = sub2(Z, pack2(zi, zi));
     const uint64_t r2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-    float dx0, dx1, dy0, dy1, dz0, dz1, r20, r21;
+    float r20, r21;
+    unpack2(r2, r20, r21);
+    const float i0 = rsqrt_ftz(r20);
+    const float i1 = rsqrt_ftz(r21);
+    if (BODY == kNp) {
+        acc2 = fma2(pack2(m0, m1), pack2(i0, i1), acc2);
+        return;
+    }
+    float dx0, dx1, dy0, dy1, dz0, dz1;
     unpack2(dx, dx0, dx1);
     unpack2(dy, dy0, dy1);
     unpack2(dz, dz0, dz1);
-    unpack2(r2, r20, r21);
-    const float t0 = min3abs(dx0, dy0, dz0);
-    const float t1 = min3abs(dx1, dy1, dz1);
-    const float i0 = rsqrt_ftz(r20);
-    const float i1 = rsqrt_ftz(r21);
-    if (t0 > 0.f) acc = fmaf(m0, i0, acc);
-    if (t1 > 0.f) acc = fmaf(m1, i1, acc);
+    bool p0, p1;
+    if (BODY == kPred) {
+        // particle_subroutines.f90:499-501: all three coordinates differ
+        p0 = min3abs(dx0, dy0, dz0) > 0.f;
+        p1 = min3abs(dx1, dy1, dz1) > 0.f;
+    } else if (BODY == kGuard) {
+        p0 = r20 > 0.f;
+        p1 = r21 > 0.f;
+    } else if (BODY == kCorrX) {
+        p0 = (dx0 == 0.f) && (r20 > 0.f);
+        p1 = (dx1 == 0.f) && (r21 > 0.f);
+    } else if (BODY == kCorrY) {
+        p0 = (dy0 == 0.f) && (dx0 != 0.f);
+        p1 = (dy1 == 0.f) && (dx1 != 0.f);
+    } else {
+        p0 = (dz0 == 0.f) && (dx0 != 0.f) && (dy0 != 0.f);
+        p1 = (dz1 == 0.f) && (dx1 != 0.f) && (dy1 != 0.f);
+    }
+    if (p0) acc = fmaf(m0, i0, acc);
+    if (p1) acc = fmaf(m1, i1, acc);
 }
 
-template <int T>
+template <int T, int BODY>
 __device__ __forceinline__ void tile_fast(const float *__restrict__ stage, int len, const float (&xi)[T],
                                           const float (&yi)[T], const float (&zi)[T], double (&acc64)[T])
 {
@@ -189,8 +259,12 @@ __device__ __forceinline__ void tile_fast(const float *__restrict__ stage, int l
     for (int qb = 0; qb < nq; qb += kFlushQuads) {
         const int qe = min(qb + kFlushQuads, nq);
         float acc[T];
+        uint64_t acc2[T];
 #pragma unroll
-        for (int t = 0; t < T; ++t) acc[t] = 0.f;
+        for (int t = 0; t < T; ++t) {
+            acc[t] = 0.f;
+            acc2[t] = 0ull;
+        }
 #pragma unroll 2
         for (int q = qb; q < qe; ++q) {
             const float4 x4 = X[q], y4 = Y[q], z4 = Z[q], m4 = M[q];
@@ -199,44 +273,183 @@ __device__ __forceinline__ void tile_fast(const float *__restrict__ stage, int l
             const uint64_t z01 = pack2(z4.x, z4.y), z23 = pack2(z4.z, z4.w);
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                pair_fast(x01, y01, z01, m4.x, m4.y, xi[t], yi[t], zi[t], acc[t]);
-                pair_fast(x23, y23, z23, m4.z, m4.w, xi[t], yi[t], zi[t], acc[t]);
+                pair_body<BODY>(x01, y01, z01, m4.x, m4.y, xi[t], yi[t], zi[t], acc[t], acc2[t]);
+                pair_body<BODY>(x23, y23, z23, m4.z, m4.w, xi[t], yi[t], zi[t], acc[t], acc2[t]);
             }
         }
 #pragma unroll
-        for (int t = 0; t < T; ++t) acc64[t] += static_cast<double>(acc[t]);
+        for (int t = 0; t < T; ++t) {
+            if (BODY == kNp) {
+                float lo, hi;
+                unpack2(acc2[t], lo, hi);
+                acc[t] = lo + hi;
+            }
+            acc64[t] += static_cast<double>(acc[t]);
+        }
     }
 }
 
-template <int T, int MINB>
+// Ring state of one warp (continues across tickets).
+struct Ring {
+    float *buf;
+    uint64_t *bars;
+    uint32_t par;
+    int fill, use;
+};
+
+// Streams every tile of `prod` through the ring and applies the body chosen per tile.
+// CTX 0: predicated main ticket; 1: predicate-free main ticket (own tile guarded);
+// 2..4: correction ticket of axis CTX-2.
+template <int T, int CTX>
+__device__ __forceinline__ void run_tiles(const PotParams &p, TileCursor prod, Ring &rg, int lane, int own_lo,
+                                          int own_hi, const float (&xi)[T], const float (&yi)[T],
+                                          const float (&zi)[T], double (&acc64)[T])
+{
+    TileCursor cons = prod;
+#pragma unroll 1
+    for (int i = 0; i < kStages - 1 && prod.valid(); ++i) {
+        issue_tile(p, prod, rg.buf + rg.fill * kStageFloats, &rg.bars[rg.fill], lane);
+        rg.fill = (rg.fill + 1 == kStages) ? 0 : rg.fill + 1;
+        prod.next();
+    }
+#pragma unroll 1
+    while (cons.valid()) {
+        if (prod.valid()) {
+            issue_tile(p, prod, rg.buf + rg.fill * kStageFloats, &rg.bars[rg.fill], lane);
+            rg.fill = (rg.fill + 1 == kStages) ? 0 : rg.fill + 1;
+            prod.next();
+        }
+        mbar_wait(&rg.bars[rg.use], (rg.par >> rg.use) & 1u);
+        rg.par ^= 1u << rg.use;
+        const float *stage = rg.buf + rg.use * kStageFloats;
+        const int len = cons.len();
+        if (CTX == 0) {
+            tile_fast<T, kPred>(stage, len, xi, yi, zi, acc64);
+        } else if (CTX == 1) {
+            // the tile that holds the group's own members can contain zero separations
+            const bool own = (cons.flags & kSegMembers) && cons.pos < own_hi && cons.pos + kTileJ > own_lo;
+            if (own)
+                tile_fast<T, kGuard>(stage, len, xi, yi, zi, acc64);
+            else
+                tile_fast<T, kNp>(stage, len, xi, yi, zi, acc64);
+        } else if (CTX == 2) {
+            tile_fast<T, kCorrX>(stage, len, xi, yi, zi, acc64);
+        } else if (CTX == 3) {
+            tile_fast<T, kCorrY>(stage, len, xi, yi, zi, acc64);
+        } else {
+            tile_fast<T, kCorrZ>(stage, len, xi, yi, zi, acc64);
+        }
+        __syncwarp();      // every lane is done with this stage before it is refilled
+        rg.use = (rg.use + 1 == kStages) ? 0 : rg.use + 1;
+        cons.next();
+    }
+}
+
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *a, int64_t lo, int64_t hi, uint32_t v)
+{
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int64_t upper_bound_u32(const uint32_t *a, int64_t lo, int64_t hi, uint32_t v)
+{
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] <= v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// Correction ticket: 32*T consecutive members of the axis-sorted order against the range of
+// sorted sources whose key lies between the first and the last of them.
+template <int T, int AXIS>
+__device__ __forceinline__ void correction_ticket(const PotParams &p, const Ticket &tk, Ring &rg, int lane)
+{
+    constexpr int kGroup = 32 * T;
+    const HaloDesc *hd = &p.halo[tk.h];
+    const SortedAxis &A = p.ax[AXIS];
+    const int n0 = hd->n0;
+    const int li0 = tk.group * kGroup;
+    float xi[T], yi[T], zi[T];
+    int slot[T];
+    double acc64[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int li = li0 + t * 32 + lane;
+        const bool ok = li < n0;
+        const int64_t k = ok ? A.tgt[hd->uoff + li] : 0;
+        xi[t] = ok ? A.x[k] : 0.f;
+        yi[t] = ok ? A.y[k] : 0.f;
+        zi[t] = ok ? A.z[k] : 0.f;
+        slot[t] = ok ? A.slot[k] : -1;
+        acc64[t] = 0.0;
+    }
+    const int64_t k_first = A.tgt[hd->uoff + li0];
+    const int64_t k_last = A.tgt[hd->uoff + min(li0 + kGroup, n0) - 1];
+    const int64_t sb = hd->sbegin, se = hd->sbegin + n0 + hd->n_ext;
+    int64_t lo = lower_bound_u32(A.key, sb, se, A.key[k_first]);
+    const int64_t hi = upper_bound_u32(A.key, sb, se, A.key[k_last]);
+    lo &= ~int64_t(3);       // 16-byte alignment for the bulk copies; sb is a multiple of 4
+    TileCursor cur;
+    cur.init_range(3 + AXIS, lo, static_cast<int>(hi - lo));
+    run_tiles<T, 2 + AXIS>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+        if (slot[t] >= 0) A.corr[slot[t]] = acc64[t];
+}
+
+template <int T, int MINB, bool NP>
 __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const PotParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LoopState *st = p.st;
     if (!st->any_active) return;
+    if (p.redo_only && !st->redo_any) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *ring = reinterpret_cast<float *>(smem_raw) + warp * (kStages * kStageFloats);
-    uint64_t *bars =
-        reinterpret_cast<uint64_t *>(smem_raw + kWarpsPerBlock * kStages * kStageFloats * 4) + warp * kStages;
+    Ring rg;
+    rg.buf = reinterpret_cast<float *>(smem_raw) + warp * (kStages * kStageFloats);
+    rg.bars = reinterpret_cast<uint64_t *>(smem_raw + kWarpsPerBlock * kStages * kStageFloats * 4) + warp * kStages;
+    rg.par = 0;
+    rg.fill = rg.use = 0;
     if (lane == 0) {
-        for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < kStages; ++i) mbar_init(&rg.bars[i], 1);
         fence_mbar_init();
     }
     __syncwarp();
 
     const int n_items = st->n_items;
     const int parity = st->parity;
-    uint32_t par = 0;         // per-stage wait parity bits
-    int fill = 0, use = 0;    // ring positions (continue across tickets)
     constexpr int kGroup = 32 * T;
 
     for (;;) {
         int item = 0;
-        if (lane == 0) item = static_cast<int>(atomicAdd(&p.st->counter, 1u));
+        if (lane == 0)
+            item = static_cast<int>(atomicAdd(p.redo_only ? &p.st->counter_redo : &p.st->counter, 1u));
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         Ticket tk;
         if (!decode_ticket<kGroup>(p, item, tk)) continue;
+        if (tk.corr_axis >= 0) {
+            if (NP) {
+                if (tk.corr_axis == 0)
+                    correction_ticket<T, 0>(p, tk, rg, lane);
+                else if (tk.corr_axis == 1)
+                    correction_ticket<T, 1>(p, tk, rg, lane);
+                else
+                    correction_ticket<T, 2>(p, tk, rg, lane);
+            }
+            continue;
+        }
+        if (p.redo_only && !p.halo_redo[tk.h]) continue;
         const HaloDesc *hd = &p.halo[tk.h];
         const int64_t tbase = p.tgt_members ? hd->poff : 0;
         const int tsel = p.tgt_members ? parity : 0;
@@ -252,31 +465,23 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
             zi[t] = ok ? p.tz[tsel][tbase + i] : 0.f;
             acc64[t] = 0.0;
         }
-
-        TileCursor prod, cons;
-        prod.init(hd, tk.S, tk.s, tk.n_tgt, parity);
-        cons = prod;
-#pragma unroll 1
-        for (int i = 0; i < kStages - 1 && prod.valid(); ++i) {
-            issue_tile(p, prod, ring + fill * kStageFloats, &bars[fill], lane);
-            fill = (fill + 1 == kStages) ? 0 : fill + 1;
-            prod.next();
-        }
-#pragma unroll 1
-        while (cons.valid()) {
-            if (prod.valid()) {
-                issue_tile(p, prod, ring + fill * kStageFloats, &bars[fill], lane);
-                fill = (fill + 1 == kStages) ? 0 : fill + 1;
-                prod.next();
+        TileCursor cur;
+        cur.init(hd, tk.S, tk.s, tk.n_tgt, parity);
+        if (NP) {
+            run_tiles<T, 1>(p, cur, rg, lane, tk.group * kGroup, tk.group * kGroup + kGroup, xi, yi, zi, acc64);
+            // zero separations outside the own tile (exact duplicates) or non-finite input:
+            // hand the halo to the predicated kernel
+            bool bad = false;
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+                bad |= (tk.group * kGroup + t * 32 + lane < tk.n_tgt) && !(fabs(acc64[t]) <= 1.7976931348623157e308);
+            if (__any_sync(0xffffffffu, bad) && lane == 0) {
+                atomicExch(&p.halo_redo[tk.h], 1);
+                atomicExch(&p.st->redo_any, 1);
             }
-            mbar_wait(&bars[use], (par >> use) & 1u);
-            par ^= 1u << use;
-            tile_fast<T>(ring + use * kStageFloats, cons.len(), xi, yi, zi, acc64);
-            __syncwarp();      // every lane is done with this stage before it is refilled
-            use = (use + 1 == kStages) ? 0 : use + 1;
-            cons.next();
+        } else {
+            run_tiles<T, 0>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
         }
-
         double *out = p.phi_part + static_cast<int64_t>(tk.s) * p.phi_stride + tbase;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -351,7 +556,7 @@ __global__ void __launch_bounds__(kPotentialBlock, 4) k_potential_exact(const Po
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         Ticket tk;
-        if (!decode_ticket<32>(p, item, tk)) continue;
+        if (!decode_ticket<32>(p, item, tk) || tk.corr_axis >= 0) continue;
         const HaloDesc *hd = &p.halo[tk.h];
         const int64_t tbase = p.tgt_members ? hd->poff : 0;
         const int tsel = p.tgt_members ? parity : 0;
@@ -405,20 +610,21 @@ __global__ void __launch_bounds__(kPotentialBlock, 4) k_potential_exact(const Po
 // ---------------------------------------------------------------------------------------
 namespace {
 
-// Shapes of the FAST kernel: T targets per lane (group = 32 T targets per ticket) and the
+// Shapes of the FAST kernels: T targets per lane (group = 32 T targets per ticket) and the
 // minimum resident blocks per SM the register allocation is held to.  Variant 0 is the
 // default; HALMA_FAST_VARIANT=<index> selects another one (tuning sweeps).
 struct FastVariant {
     int targets, min_blocks;
-    void (*kernel)(const PotParams);
+    void (*pred)(const PotParams);
+    void (*np)(const PotParams);
 };
 
+#define HALMA_VARIANT(T, B) {T, B, k_potential_fast<T, B, false>, k_potential_fast<T, B, true>}
 const FastVariant kVariants[] = {
-    {4, 6, k_potential_fast<4, 6>}, {4, 5, k_potential_fast<4, 5>}, {4, 4, k_potential_fast<4, 4>},
-    {2, 8, k_potential_fast<2, 8>}, {2, 6, k_potential_fast<2, 6>}, {3, 5, k_potential_fast<3, 5>},
-    {3, 6, k_potential_fast<3, 6>}, {6, 3, k_potential_fast<6, 3>}, {8, 2, k_potential_fast<8, 2>},
-    {2, 10, k_potential_fast<2, 10>}, {1, 12, k_potential_fast<1, 12>},
+    HALMA_VARIANT(4, 6), HALMA_VARIANT(4, 5), HALMA_VARIANT(4, 4), HALMA_VARIANT(2, 8),
+    HALMA_VARIANT(3, 6), HALMA_VARIANT(6, 3), HALMA_VARIANT(8, 3),
 };
+#undef HALMA_VARIANT
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 const FastVariant &fast_variant()
@@ -445,17 +651,26 @@ cudaError_t potential_configure(int mode, int *blocks_per_sm)
                                                              kSmemBytes);
     }
     const FastVariant &v = fast_variant();
-    e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    e = cudaFuncSetAttribute(v.pred, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, v.kernel, kPotentialBlock, kSmemBytes);
+    e = cudaFuncSetAttribute(v.np, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    int a = 0, b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, v.pred, kPotentialBlock, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, v.np, kPotentialBlock, kSmemBytes);
+    *blocks_per_sm = a < b ? a : b;
+    return e;
 }
 
 cudaError_t potential_launch(const PotParams &p, int mode, int grid_blocks, cudaStream_t stream)
 {
     if (mode == HALMA_MODE_EXACT)
         k_potential_exact<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
+    else if (p.np_enabled && !p.redo_only)
+        fast_variant().np<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else
-        fast_variant().kernel<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
+        fast_variant().pred<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -95,6 +95,49 @@ def test_fast_mode_against_f64acc_and_reference_arithmetic():
         np.testing.assert_allclose(r.com, o64.com, rtol=1e-6)
 
 
+def test_gas_layout_fast_lattice_exclusions():
+    # lattice gas: ~10 % of the pairs share a coordinate; the predicate-free path must take
+    # exactly those out again (correction tickets)
+    s, g, d = case(3000, 6000, 400, extra=6)
+    vb = O.CM_velocity(O.total_mass(np.arange(len(s)), s.mass), np.arange(len(s)), s.vx, s.vy, s.vz, s.mass)
+    kw = dict(post=[d.pos_mass(), s.pos_mass()], split_classes=True, kappa=2.0, vb_fixed=vb)
+    o = O.unbind_halo(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass, variant="f64acc", **kw)
+    r = unbind_halo(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass, mode="fast", **kw)
+    assert o.n_iter >= 2
+    both = r.mask & o.mask
+    assert np.abs(r.be32[both].astype(np.float64) / o.be32[both] - 1).max() < FAST_RTOL
+    diff = r.mask != o.mask
+    assert np.all(O.energy_margin(o.energy, o.be32, 2.0)[diff] < BAND)
+    first = np.abs(r.be32.astype(np.float64)[~o.mask & (o.be32 > 0)] / o.be32[~o.mask & (o.be32 > 0)] - 1)
+    assert first.size == 0 or first.max() < FAST_RTOL          # particles removed in earlier passes too
+
+
+def test_exact_duplicates_and_signed_zero_fast():
+    # exact duplicates far apart in index (different tiles) give zero separations the
+    # predicate-free path cannot handle: the halo must be recomputed with the predicate.
+    rng = np.random.default_rng(12)
+    p = synth.plummer_stars(700, 2e-3, 1e6, rng, centre=(0.0, 0.0, 0.0), bulk_v=(0., 0., 0.))
+    for a, b in ((3, 500), (10, 650), (300, 301)):
+        p.x[b], p.y[b], p.z[b] = p.x[a], p.y[a], p.z[a]
+    p.x[40], p.x[600] = 0.0, -0.0                 # -0 == +0 for the reference's /= test
+    p.y[41], p.y[333] = -0.0, 0.0
+    o = O.unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, kappa=9.0, variant="f64acc")
+    r = unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, kappa=9.0, mode="fast")
+    assert np.all(np.isfinite(r.be32))
+    both = r.mask & o.mask
+    assert np.abs(r.be32[both].astype(np.float64) / o.be32[both] - 1).max() < FAST_RTOL
+    diff = r.mask != o.mask
+    assert np.all(O.energy_margin(o.energy, o.be32, 9.0)[diff] < BAND)
+    # the same without duplicates but with signed zeros only (no fallback needed)
+    q = synth.plummer_stars(700, 2e-3, 1e6, rng, centre=(0.0, 0.0, 0.0), bulk_v=(0., 0., 0.))
+    q.x[40], q.x[600] = 0.0, -0.0
+    q.z[5], q.z[6], q.z[7] = 0.0, -0.0, 0.0
+    o = O.unbind_halo(q.x, q.y, q.z, q.vx, q.vy, q.vz, q.mass, kappa=9.0, variant="f64acc")
+    r = unbind_halo(q.x, q.y, q.z, q.vx, q.vy, q.vz, q.mass, kappa=9.0, mode="fast")
+    both = r.mask & o.mask
+    assert np.abs(r.be32[both].astype(np.float64) / o.be32[both] - 1).max() < FAST_RTOL
+
+
 def ragged_catalogue():
     rng = np.random.default_rng(77)
     sizes = [0, 1, 2, 3, 4, 5, 31, 32, 33, 127, 128, 129, 255, 256, 257, 600, 1025, 0, 40, 2048, 7, 300]
