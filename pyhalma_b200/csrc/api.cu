@@ -575,6 +575,15 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     P->n_chunks = static_cast<int>(chunk_halo.size());
     P->n_tot = P->n_pad + P->n_ext_pad;
     if (P->n_tot > 0x7ffffff0ll || P->n_spad > 0x7ffffff0ll || P->n_user == 0) P->np = false;
+    {
+        // The predicate-free path pays off once a pass is throughput-bound; below that its
+        // extra tickets and launch only add latency (profiles/ncu_np_r01.md).
+        double pairs = 0.0;
+        for (int64_t h = 0; h < nh; ++h) pairs += static_cast<double>(halo[h].n0) * (halo[h].n0 + halo[h].n_ext);
+        const char *e = getenv("HALMA_NP_MIN_PAIRS");
+        const double min_pairs = e ? atof(e) : 4e9;
+        if (pairs < min_pairs) P->np = false;
+    }
 
     std::vector<int32_t> order(nh);
     std::iota(order.begin(), order.end(), 0);
