@@ -531,7 +531,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     int64_t poff = 0, eoff = 0, soff = 0, doff = 0;
     {
         const char *e = getenv("HALMA_NP");
-        P->np = cfg.mode == HALMA_MODE_FAST && cfg.n_ranks == 1 && !(e && atoi(e) == 0);
+        P->np = cfg.mode == HALMA_MODE_FAST && !(e && atoi(e) == 0);
     }
     for (int64_t h = 0; h < nh; ++h) {
         HaloDesc &d = halo[h];
@@ -930,6 +930,13 @@ static int enqueue_pass(halma_plan *P, int pass)
     CU_TRY(potential_launch(P->pp, P->cfg.mode, grid, s));
     if (P->np) {
         // haloes whose predicate-free sums came out non-finite are recomputed with the predicate
+        if (P->cfg.n_ranks > 1) {
+            // split mode: every rank must take the same decision
+            int e = g_nccl.AllReduce(P->d_redo.p, P->d_redo.p, static_cast<size_t>(P->n_halo), /*ncclInt32*/ 2,
+                                     /*ncclMax*/ 2, P->comm, s);
+            if (e) return nccl_fail(e, "ncclAllReduce(flags)");
+            CU_TRY(launch_sync_redo(P->lp, s));
+        }
         PotParams redo = P->pp;
         redo.redo_only = 1;
         CU_TRY(potential_launch(redo, P->cfg.mode, grid, s));
@@ -999,7 +1006,7 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
             ++passes;
             if (!still) done = true;
         }
-        launches += queued * (5 + (P->cfg.n_ranks > 1 ? 2 : 0) + (P->np ? 1 : 0));
+        launches += queued * (5 + (P->cfg.n_ranks > 1 ? 2 : 0) + (P->np ? (P->cfg.n_ranks > 1 ? 2 : 1) : 0));
         pot_launches = queued;
         CU_TRY(launch_finalize(P->lp, sm, s));
         ++launches;

@@ -453,6 +453,17 @@ __global__ void __launch_bounds__(256) k_fold_partials(const LoopParams p)
     }
 }
 
+// Split mode, predicate-free path: after the max-all-reduce of the per-halo fallback flags
+// every rank derives the same redo_any.
+__global__ void k_sync_redo(const LoopParams p)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int any = 0;
+        for (int h = 0; h < p.n_halo; ++h) any |= p.halo_redo[h];
+        p.st->redo_any = any;
+    }
+}
+
 // After the all-reduce plane 0 holds the complete Phi: tell k_energy_flag to read only it.
 __global__ void k_set_nsplit_one(const LoopParams p)
 {
@@ -532,6 +543,12 @@ cudaError_t launch_schedule(const LoopParams &p, int init, cudaStream_t s)
 cudaError_t launch_fold_partials(const LoopParams &p, int sm_count, cudaStream_t s)
 {
     k_fold_partials<<<chunk_grid(p, sm_count), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sync_redo(const LoopParams &p, cudaStream_t s)
+{
+    k_sync_redo<<<1, 32, 0, s>>>(p);
     return cudaGetLastError();
 }
 

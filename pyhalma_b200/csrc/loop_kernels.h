@@ -55,6 +55,7 @@ cudaError_t launch_halo_decide(const LoopParams &p, int init, int sm_count, cuda
 cudaError_t launch_compact(const LoopParams &p, int sm_count, cudaStream_t s);
 cudaError_t launch_schedule(const LoopParams &p, int init, cudaStream_t s);
 cudaError_t launch_fold_partials(const LoopParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_sync_redo(const LoopParams &p, cudaStream_t s);
 cudaError_t launch_set_nsplit_one(const LoopParams &p, cudaStream_t s);
 cudaError_t launch_finalize(const LoopParams &p, int sm_count, cudaStream_t s);
 

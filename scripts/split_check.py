@@ -16,7 +16,7 @@ rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000)):
+for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000), ("fast", 90000, 40000)):
     c = synth.config1(n_star, n_gas, n_dm=500)
     s, g, d = c.stars, c.gas, c.dm
     uid = [nccl_unique_id() if rank == 0 else None]
