@@ -95,9 +95,10 @@ int halma_potential_f32_dev(int device, int mode,
  * Source order / classes per halo:
  *   split_classes = 0 (stellar, halo_properties.py:333-339): one in-order sum over
  *       ext group 0 .. n_pre-1, members, ext group n_pre .. n_groups-1.
- *   split_classes = 1 (gas, halo_gas.py:301-450): members first, then each ext group,
- *       every class summed on its own and the class sums added in float32 in that order
- *       (n_pre must be 0).
+ *   split_classes = 1 (gas, halo_gas.py:301-450; most_bound_particle, :508-622): the same
+ *       order, but every group and the members are summed on their own and the class sums
+ *       are added in float32 in that order (gas: n_pre = 0, members first; most-bound:
+ *       n_pre = n_groups, members last).
  * Energy and mask per pass (halo_properties.py:342-359 / halo_gas.py:456-476):
  *       pe = -(float)Phi; pe *= (float)G; pe *= (float)kappa        (float32)
  *       E  = 0.5*((vx-vbx)^2 + (vy-vby)^2 + (vz-vbz)^2) + pe        (float64)
@@ -136,6 +137,13 @@ typedef struct halma_halo_result {
     double  com[3];          /* centre of mass                  (halo_properties.py:26)  */
     double  vb[3];           /* bulk velocity used by the last pass / of the bound set   */
     int64_t pairs;           /* (target, source) pairs evaluated over all passes         */
+    int64_t most_bound;      /* local index of the member of the LAST pass with the largest
+                                sum m/r, lowest index on ties (halo_gas.py:627-632: argmin of
+                                the negated potential); -1 if no pass was made            */
+    double  mass_initial;    /* sum m over all members                  (halo_gas.py:483) */
+    double  cold_bound_mass; /* T <  cold_T and bound at the end        (halo_gas.py:484) */
+    double  unbound_cold_mass; /* T <  cold_T and removed in some pass  (halo_gas.py:489) */
+    double  unbound_hot_mass;  /* T >= cold_T and removed in some pass  (halo_gas.py:490) */
 } halma_halo_result;
 
 typedef struct halma_run_stats {
@@ -161,6 +169,9 @@ int halma_plan_upload_members(halma_plan *plan, const double *x, const double *y
                               const double *mass);
 int halma_plan_upload_group(halma_plan *plan, int group, const double *mass, const double *x,
                             const double *y, const double *z);
+/* Optional member temperatures (double[N]) for the cold / hot mass sums of RPS
+ * (halo_gas.py:479-492); cold means T < cold_T (5e4 K in the reference). */
+int halma_plan_upload_temp(halma_plan *plan, const double *temp, double cold_T);
 /* vb: double[3*n_halo]; required when vb_fixed = 1. */
 int halma_plan_set_vb(halma_plan *plan, const double *vb);
 

@@ -21,7 +21,7 @@ EXPORTS = (
     "halma_last_error", "halma_abi_version", "halma_device_count", "halma_device_info",
     "halma_host_alloc", "halma_host_free", "halma_potential_f32", "halma_potential_workspace_bytes",
     "halma_potential_f32_dev", "halma_plan_create", "halma_plan_destroy", "halma_plan_upload_members",
-    "halma_plan_upload_group", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join",
+    "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join",
     "halma_plan_run", "halma_plan_download", "halma_unbind_halo", "halma_microbench",
 )
 
@@ -43,7 +43,9 @@ class UnbindConfig(C.Structure):
 class HaloResult(C.Structure):
     _fields_ = [("n_bound", C.c_int64), ("n_iter", C.c_int32), ("converged", C.c_int32),
                 ("mass", C.c_double), ("com", C.c_double * 3), ("vb", C.c_double * 3),
-                ("pairs", C.c_int64)]
+                ("pairs", C.c_int64), ("most_bound", C.c_int64), ("mass_initial", C.c_double),
+                ("cold_bound_mass", C.c_double), ("unbound_cold_mass", C.c_double),
+                ("unbound_hot_mass", C.c_double)]
 
 
 class RunStats(C.Structure):
@@ -83,6 +85,7 @@ def lib() -> C.CDLL:
     L.halma_plan_destroy.restype = None
     L.halma_plan_upload_members.argtypes = [vp] + [vp] * 7
     L.halma_plan_upload_group.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.halma_plan_upload_temp.argtypes = [vp, vp, C.c_double]
     L.halma_plan_set_vb.argtypes = [vp, vp]
     L.halma_nccl_unique_id.argtypes = [vp]
     L.halma_plan_join.argtypes = [vp, vp]

@@ -437,7 +437,12 @@ struct halma_plan {
     DBuf<double> d_hdbl;                  // per-halo doubles: M(1) vb(3) vb_next(3) com(3)
     DBuf<unsigned long long> d_pairs;
     DBuf<int32_t> d_cint;                 // per-chunk ints: cnt, off
-    DBuf<double> d_csum;                  // 7 per chunk
+    DBuf<double> d_csum;                  // kChunkSums per chunk
+    DBuf<float> d_cbest;
+    DBuf<int32_t> d_cbestq, d_hbest;
+    DBuf<double> d_hrps, d_temp;
+    bool temp_up = false;
+    double cold_T = 5e4;
     DBuf<uint8_t> d_flag, d_mask;
     DBuf<float> d_be;
     DBuf<double> d_E;
@@ -472,6 +477,7 @@ struct halma_plan {
         d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_cint.release();
         d_csum.release(); d_flag.release(); d_mask.release(); d_be.release(); d_E.release();
         d_idx.release(); d_phi.release(); d_st.release();
+        d_cbest.release(); d_cbestq.release(); d_hbest.release(); d_hrps.release(); d_temp.release();
         d_src_halo.release(); d_sslot.release(); d_stgt.release(); d_sinv.release(); d_redo.release();
         d_nsel.release(); d_keys.release(); d_ids.release(); d_skey.release(); d_ismem.release();
         d_sorttemp.release(); d_sf.release(); d_corr.release();
@@ -517,14 +523,8 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
 
     // segment order (see include/halma_unbind.h): which HaloDesc::seg slot each group lands in
     P->group_seg.assign(cfg.n_groups, 0);
-    int members_slot;
-    if (cfg.split_classes) {
-        members_slot = 0;
-        for (int g = 0; g < cfg.n_groups; ++g) P->group_seg[g] = 1 + g;
-    } else {
-        members_slot = cfg.n_pre;
-        for (int g = 0; g < cfg.n_groups; ++g) P->group_seg[g] = g < cfg.n_pre ? g : g + 1;
-    }
+    const int members_slot = cfg.n_pre;
+    for (int g = 0; g < cfg.n_groups; ++g) P->group_seg[g] = g < cfg.n_pre ? g : g + 1;
 
     std::vector<HaloDesc> halo(nh);
     std::vector<int32_t> chunk_halo, chunk_p0;
@@ -622,7 +622,12 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(P->d_hdbl.alloc(10 * nh));
     CU_TRY(P->d_pairs.alloc(nh));
     CU_TRY(P->d_cint.alloc(2 * static_cast<size_t>(P->n_chunks)));
-    CU_TRY(P->d_csum.alloc(7 * static_cast<size_t>(P->n_chunks)));
+    CU_TRY(P->d_csum.alloc(kChunkSums * static_cast<size_t>(P->n_chunks)));
+    CU_TRY(P->d_cbest.alloc(static_cast<size_t>(P->n_chunks)));
+    CU_TRY(P->d_cbestq.alloc(static_cast<size_t>(P->n_chunks)));
+    CU_TRY(P->d_hrps.alloc(4 * nh));
+    CU_TRY(P->d_hbest.alloc(nh));
+    CU_TRY(P->d_temp.alloc(NU));
     CU_TRY(P->d_flag.alloc(NP));
     CU_TRY(P->d_mask.alloc(NU));
     CU_TRY(P->d_be.alloc(NU));
@@ -719,6 +724,12 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.chunk_cnt = P->d_cint.p;
     L.chunk_off = P->d_cint.p + P->n_chunks;
     L.chunk_sum = P->d_csum.p;
+    L.chunk_best = P->d_cbest.p;
+    L.chunk_best_q = P->d_cbestq.p;
+    L.temp = nullptr;
+    L.cold_T = 5e4;
+    L.hrps = P->d_hrps.p;
+    L.hbest = P->d_hbest.p;
     L.flag = P->d_flag.p;
     L.out_mask = P->d_mask.p;
     L.out_be = P->d_be.p;
@@ -827,7 +838,6 @@ extern "C" int halma_plan_create(const halma_unbind_config *cfg, int64_t n_halo,
     if (n_halo < 0 || n_halo > 0x7ffffff0ll) return fail(HALMA_ERR_INVALID, "bad n_halo");
     if (cfg->n_groups < 0 || cfg->n_groups > HALMA_MAX_GROUPS) return fail(HALMA_ERR_INVALID, "bad n_groups");
     if (cfg->n_pre < 0 || cfg->n_pre > cfg->n_groups) return fail(HALMA_ERR_INVALID, "bad n_pre");
-    if (cfg->split_classes && cfg->n_pre != 0) return fail(HALMA_ERR_INVALID, "split_classes requires n_pre = 0");
     if (cfg->max_iter < 1 || cfg->max_iter > 4096) return fail(HALMA_ERR_INVALID, "max_iter must be in 1..4096");
     if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) return fail(HALMA_ERR_INVALID, "bad rank");
     if (cfg->n_ranks > 1 && n_halo != 1) return fail(HALMA_ERR_INVALID, "split mode shares exactly one halo");
@@ -896,6 +906,21 @@ extern "C" int halma_plan_upload_group(halma_plan *P, int group, const double *m
     }
     P->group_up[group] = true;
     P->sorted_dirty = true;
+    return HALMA_OK;
+}
+
+extern "C" int halma_plan_upload_temp(halma_plan *P, const double *temp, double cold_T)
+{
+    if (!P) return fail(HALMA_ERR_INVALID, "null plan");
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    if (P->n_user) {
+        if (!temp) return fail(HALMA_ERR_INVALID, "null temperature array");
+        CU_TRY(cudaMemcpyAsync(P->d_temp.p, temp, P->n_user * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+    }
+    P->temp_up = true;
+    P->cold_T = cold_T;
+    P->lp.temp = P->d_temp.p;
+    P->lp.cold_T = cold_T;
     return HALMA_OK;
 }
 
@@ -1058,6 +1083,10 @@ extern "C" int halma_plan_download(halma_plan *P, uint8_t *mask, float *be, doub
         std::vector<int32_t> hi(P->d_hint.n);
         std::vector<double> hd(P->d_hdbl.n);
         std::vector<unsigned long long> pr(nh);
+        std::vector<double> rps(4 * nh);
+        std::vector<int32_t> best(nh);
+        CU_TRY(cudaMemcpyAsync(rps.data(), P->d_hrps.p, rps.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(best.data(), P->d_hbest.p, nh * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaMemcpyAsync(hi.data(), P->d_hint.p, hi.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaMemcpyAsync(hd.data(), P->d_hdbl.p, hd.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaMemcpyAsync(pr.data(), P->d_pairs.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -1073,6 +1102,11 @@ extern "C" int halma_plan_download(halma_plan *P, uint8_t *mask, float *be, doub
                 r.com[k] = hd[7 * nh + 3 * h + k];
             }
             r.pairs = static_cast<int64_t>(pr[h]);
+            r.most_bound = best[h];
+            r.mass_initial = rps[4 * h];
+            r.cold_bound_mass = P->temp_up ? rps[4 * h + 1] : 0.0;
+            r.unbound_cold_mass = P->temp_up ? rps[4 * h + 2] : 0.0;
+            r.unbound_hot_mass = P->temp_up ? rps[4 * h + 3] : 0.0;
         }
     }
     CU_TRY(cudaStreamSynchronize(s));

@@ -90,12 +90,12 @@ __device__ __forceinline__ int my_groups(int n, int gs, int rank, int n_ranks)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCh) k_pack_members(const LoopParams p)
 {
-    __shared__ double red[7 * (kCh / 32)];
+    __shared__ double red[kChunkSums * (kCh / 32)];
     for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
         const int h = p.chunk_halo[c];
         const HaloDesc &hd = p.halo[h];
         const int q = p.chunk_p0[c] + threadIdx.x;
-        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        double s[kChunkSums] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (q < hd.n0) {
             const int64_t i = hd.poff + q, g = hd.uoff + q;
             const double x = p.x64[g], y = p.y64[g], z = p.z64[g], m = p.m64[g];
@@ -112,11 +112,13 @@ __global__ void __launch_bounds__(kCh) k_pack_members(const LoopParams p)
             s[5] = m * y;
             s[6] = m * z;
         }
-        block_sum<7>(s, red);
+        block_sum<kChunkSums>(s, red);
         if (threadIdx.x == 0) {
             p.chunk_cnt[c] = min(kCh, max(hd.n0 - p.chunk_p0[c], 0));
 #pragma unroll
-            for (int k = 0; k < 7; ++k) p.chunk_sum[static_cast<int64_t>(c) * 7 + k] = s[k];
+            for (int k = 0; k < kChunkSums; ++k) p.chunk_sum[static_cast<int64_t>(c) * kChunkSums + k] = s[k];
+            p.chunk_best[c] = -1.f;
+            p.chunk_best_q[c] = -1;
         }
     }
 }
@@ -144,7 +146,9 @@ __global__ void __launch_bounds__(256) k_pack_group(const HaloDesc *halo, int n_
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
 {
-    __shared__ double red[7 * (kCh / 32)];
+    __shared__ double red[kChunkSums * (kCh / 32)];
+    __shared__ float sbest[kCh / 32];
+    __shared__ int sbest_q[kCh / 32];
     if (!p.st->any_active) return;
     const int par = p.st->parity;
     for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
@@ -155,8 +159,10 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
         if (p0 >= n) continue;
         const HaloDesc &hd = p.halo[h];
         const int q = p0 + threadIdx.x;
-        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        double s[kChunkSums] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         int bound = 0;
+        float best = -1.f;          // potentials are >= 0; NaN never wins
+        int best_q = -1;
         if (q < n) {
             const int64_t i = hd.poff + q;
             const int64_t g = p.widx[par][i];
@@ -186,6 +192,18 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
             p.out_mask[g] = static_cast<uint8_t>(bound);
             p.out_be[g] = be;
             p.out_E[g] = E;
+            if (be > best) {
+                best = be;
+                best_q = static_cast<int>(g - hd.uoff);
+            }
+            if (p.temp) {
+                // halo_gas.py:479-490: cold = T < 5e4, hot = T >= 5e4 (NaN is neither)
+                const double T = p.temp[g], m = p.m64[g];
+                const bool cold = T < p.cold_T, hot = T >= p.cold_T;
+                if (bound && cold) s[7] = m;
+                if (E > 0.0 && cold) s[8] = m;
+                if (E > 0.0 && hot) s[9] = m;
+            }
             if (bound) {
                 const double m = p.m64[g];
                 s[0] = m;
@@ -198,12 +216,34 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
             }
         }
         const int count = __syncthreads_count(bound);
-        block_sum<7>(s, red);
+        block_sum<kChunkSums>(s, red);
+        // most bound member of the chunk: largest potential, lowest index on ties
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_down_sync(0xffffffffu, best, o);
+            const int oq = __shfl_down_sync(0xffffffffu, best_q, o);
+            if (ob > best || (ob == best && oq >= 0 && (best_q < 0 || oq < best_q))) {
+                best = ob;
+                best_q = oq;
+            }
+        }
+        if ((threadIdx.x & 31) == 0) {
+            sbest[threadIdx.x >> 5] = best;
+            sbest_q[threadIdx.x >> 5] = best_q;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
             p.chunk_cnt[c] = count;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) p.chunk_sum[static_cast<int64_t>(c) * 7 + k] = s[k];
+            for (int k = 0; k < kChunkSums; ++k) p.chunk_sum[static_cast<int64_t>(c) * kChunkSums + k] = s[k];
+            for (int w = 1; w < kCh / 32; ++w)
+                if (sbest[w] > best || (sbest[w] == best && sbest_q[w] >= 0 && (best_q < 0 || sbest_q[w] < best_q))) {
+                    best = sbest[w];
+                    best_q = sbest_q[w];
+                }
+            p.chunk_best[c] = best;
+            p.chunk_best_q[c] = best_q;
         }
+        __syncthreads();
     }
 }
 
@@ -214,7 +254,7 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
 __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int init)
 {
     __shared__ int sscan[kCh / 32 + 1];
-    __shared__ double red[7 * (kCh / 32)];
+    __shared__ double red[kChunkSums * (kCh / 32)];
     if (!init && !p.st->any_active) return;
     for (int h = blockIdx.x; h < p.n_halo; h += gridDim.x) {
         if (!init && !p.active[h]) continue;
@@ -222,7 +262,9 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
         const int n_old = init ? hd.n0 : p.cnt[h];
         const int nch = (n_old + kCh - 1) / kCh;
         int carry = 0;
-        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        double s[kChunkSums] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float best = -1.f;          // most bound member of this pass (largest potential, lowest index)
+        int best_q = -1;
         for (int c0 = 0; c0 < nch; c0 += kCh) {
             const int c = c0 + threadIdx.x;
             const int v = (c < nch) ? p.chunk_cnt[hd.chunk_begin + c] : 0;
@@ -230,16 +272,54 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
             const int ex = block_exclusive_scan(v, sscan, total);
             if (c < nch) {
                 p.chunk_off[hd.chunk_begin + c] = carry + ex;
-                const double *cs = p.chunk_sum + static_cast<int64_t>(hd.chunk_begin + c) * 7;
+                const double *cs = p.chunk_sum + static_cast<int64_t>(hd.chunk_begin + c) * kChunkSums;
 #pragma unroll
-                for (int k = 0; k < 7; ++k) s[k] += cs[k];
+                for (int k = 0; k < kChunkSums; ++k) s[k] += cs[k];
+                const float b = p.chunk_best[hd.chunk_begin + c];
+                const int bq = p.chunk_best_q[hd.chunk_begin + c];
+                if (b > best || (b == best && bq >= 0 && (best_q < 0 || bq < best_q))) {
+                    best = b;
+                    best_q = bq;
+                }
             }
             carry += total;
         }
-        block_sum<7>(s, red);
+        // block-wide (value, index) reduction with the same tie rule
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_down_sync(0xffffffffu, best, o);
+            const int oq = __shfl_down_sync(0xffffffffu, best_q, o);
+            if (ob > best || (ob == best && oq >= 0 && (best_q < 0 || oq < best_q))) {
+                best = ob;
+                best_q = oq;
+            }
+        }
+        __shared__ float hb[kCh / 32];
+        __shared__ int hq[kCh / 32];
+        if ((threadIdx.x & 31) == 0) {
+            hb[threadIdx.x >> 5] = best;
+            hq[threadIdx.x >> 5] = best_q;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 1; w < kCh / 32; ++w)
+                if (hb[w] > best || (hb[w] == best && hq[w] >= 0 && (best_q < 0 || hq[w] < best_q))) {
+                    best = hb[w];
+                    best_q = hq[w];
+                }
+        block_sum<kChunkSums>(s, red);
         if (threadIdx.x == 0) {
             const int n_new = carry;
             const double M = s[0];
+            if (init) {
+                p.hrps[4 * h + 0] = M;
+                p.hrps[4 * h + 1] = p.hrps[4 * h + 2] = p.hrps[4 * h + 3] = 0.0;
+                p.hbest[h] = -1;
+            } else {
+                p.hrps[4 * h + 1] = s[7];            // cold members bound after this pass
+                p.hrps[4 * h + 2] += s[8];           // removed, cold
+                p.hrps[4 * h + 3] += s[9];           // removed, hot
+                p.hbest[h] = best_q;
+            }
             p.hM[h] = M;
             const double inv = M > 0.0 ? 1.0 / M : 0.0;
             // halo_properties.py:39-43, 56-60: sums divided by M, zeros when M == 0

@@ -8,6 +8,7 @@
 namespace halma {
 
 constexpr int kChunk = 256;               // members per bookkeeping chunk
+constexpr int kChunkSums = 10;            // float64 sums kept per chunk
 constexpr int kMinSplitSources = 2048;    // never split a halo's sources into pieces below this
 constexpr int kMaxSplit = 8;              // planes of the partial-potential buffer
 constexpr int kNominalTickets = 32768;    // j-split aims at this many tickets per pass (machine-independent)
@@ -29,7 +30,14 @@ struct LoopParams {
     unsigned long long *pairs;
     // per-chunk scratch
     int32_t *chunk_cnt, *chunk_off;
-    double *chunk_sum;                    // 7 per chunk: m, m*v[3], m*x[3]
+    double *chunk_sum;                    // kChunkSums per chunk: m, m*v[3], m*x[3] of the survivors,
+                                          // cold survivors' m, removed cold m, removed hot m
+    float *chunk_best;                    // per chunk: largest potential of the pass ...
+    int32_t *chunk_best_q;                // ... and the member position that has it
+    const double *temp;                   // optional member temperatures (user layout)
+    double cold_T;
+    double *hrps;                         // 4 per halo: initial M, cold bound, unbound cold, unbound hot
+    int32_t *hbest;                       // per halo: user-local index of the most bound member
     // per-particle
     uint8_t *flag;                        // [n_pad] bound flag of the current pass
     uint8_t *out_mask;                    // [n_user]

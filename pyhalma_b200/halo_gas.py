@@ -138,14 +138,32 @@ def RPS(gas_x, gas_y, gas_z, gas_vx, gas_vy, gas_vz, gas_mass, gas_temp,  # noqa
 
 def most_bound_particle(gas_x, gas_y, gas_z, gas_mass, dm_x, dm_y, dm_z, dm_mass,
                         st_x, st_y, st_z, st_mass, st_oripa, BRUTE_FORCE_LIM, mass_dm_part,
-                        *, mode=None, device=0):
+                        *, mode=None, device=0, fused=True):
     """Position and id of the star at the potential minimum (halo_gas.py:498-634).  Class
-    order: gas, heavy DM, light DM, stars; the DM split is unconditional here (:548)."""
+    order: gas, heavy DM, light DM, stars; the DM split is unconditional here (:548).
+
+    fused=True (and no class above BRUTE_FORCE_LIM): one device-resident plan evaluates the
+    four classes and the arg-min on the GPU; otherwise one kernel call per class and a host
+    arg-min, like the reference."""
     nst = len(st_x)
-    binding_energy = np.zeros((nst,), dtype=np.float32)
     mode = _lib.default_mode() if mode is None else _lib.mode_code(mode)
-    _class_sum(binding_energy, gas_mass, gas_x, gas_y, gas_z, st_x, st_y, st_z, BRUTE_FORCE_LIM, mode, device)
     heavy, light = _split_dm(dm_x, dm_y, dm_z, dm_mass, mass_dm_part)
+    sampled = (len(gas_x) > BRUTE_FORCE_LIM or len(light[0]) > BRUTE_FORCE_LIM or nst > BRUTE_FORCE_LIM)
+    if fused and not sampled and nst > 0:
+        ext = [(gas_mass, gas_x, gas_y, gas_z), (heavy[3], heavy[0], heavy[1], heavy[2]),
+               (light[3], light[0], light[1], light[2])]
+        zeros = np.zeros(nst)
+        with UnbindPlan(np.array([0, nst], np.int64), [np.array([0, len(g[0])], np.int64) for g in ext], mode=mode,
+                        n_pre=3, split_classes=True, vb_fixed=True, max_iter=1, kappa=1.0, device=device) as plan:
+            plan.upload_members(st_x, st_y, st_z, zeros, zeros, zeros, st_mass)
+            for k, g in enumerate(ext):
+                plan.upload_group(k, g[0], g[1], g[2], g[3])
+            plan.set_vb([0., 0., 0.])
+            plan.run()
+            k = plan.download(mask=False, be=False, energy=False, idx=False).halos[0].most_bound
+        return st_x[k], st_y[k], st_z[k], st_oripa[k]
+    binding_energy = np.zeros((nst,), dtype=np.float32)
+    _class_sum(binding_energy, gas_mass, gas_x, gas_y, gas_z, st_x, st_y, st_z, BRUTE_FORCE_LIM, mode, device)
     _class_sum(binding_energy, heavy[3], heavy[0], heavy[1], heavy[2], st_x, st_y, st_z, np.inf, mode, device)
     _class_sum(binding_energy, light[3], light[0], light[1], light[2], st_x, st_y, st_z, BRUTE_FORCE_LIM,
                mode, device)

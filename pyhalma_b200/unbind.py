@@ -49,6 +49,11 @@ class HaloResult:
     com: tuple
     vb: tuple
     pairs: int
+    most_bound: int = -1              # local index of the member with the deepest potential (last pass)
+    mass_initial: float = 0.0
+    cold_bound_mass: float = 0.0      # needs upload_temp
+    unbound_cold_mass: float = 0.0
+    unbound_hot_mass: float = 0.0
 
 
 @dataclass
@@ -172,6 +177,14 @@ class UnbindPlan:
         self._keep.append(arrs)
         _lib.check(self._L.halma_plan_upload_group(self._h, group, *[a.ctypes.data for a in arrs]))
 
+    def upload_temp(self, temp, cold_T: float = 5 * 1e4):
+        """Member temperatures for the cold / hot mass sums of RPS (halo_gas.py:479-492)."""
+        t = _f64(temp)
+        if len(t) != self.n:
+            raise ValueError("temp must have offsets[-1] entries")
+        self._keep.append([t])
+        _lib.check(self._L.halma_plan_upload_temp(self._h, t.ctypes.data, float(cold_T)))
+
     def set_vb(self, vb):
         vb = np.ascontiguousarray(vb, dtype=np.float64).reshape(-1)
         if len(vb) != 3 * self.n_halo:
@@ -206,7 +219,9 @@ class UnbindPlan:
             for h in range(self.n_halo):
                 r = hr[h]
                 out.append(HaloResult(int(r.n_bound), int(r.n_iter), bool(r.converged), float(r.mass),
-                                      tuple(r.com), tuple(r.vb), int(r.pairs)))
+                                      tuple(r.com), tuple(r.vb), int(r.pairs), int(r.most_bound),
+                                      float(r.mass_initial), float(r.cold_bound_mass),
+                                      float(r.unbound_cold_mass), float(r.unbound_hot_mass)))
         return CatalogueResult(self.offsets, m, b, e, i, out)
 
 
@@ -219,11 +234,13 @@ def nccl_unique_id() -> bytes:
 
 def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (), n_pre: int = 0,
                      split_classes: bool = False, vb=None, kappa: float = 9.0, max_iter: int = 64,
-                     mode="fast", device: int = 0, G: float = G_CONST) -> CatalogueResult:
+                     mode="fast", device: int = 0, G: float = G_CONST, temp=None,
+                     cold_T: float = 5 * 1e4) -> CatalogueResult:
     """Unbind every halo of a catalogue in one batched, device-resident run.
 
     groups: sequence of (ext_offsets, mass, x, y, z) external source groups.
     vb: None (bulk velocity recomputed from the bound set each pass) or float64[n_halo, 3].
+    temp: optional member temperatures; fills the cold / hot mass sums of every HaloResult.
     """
     plan = UnbindPlan(offsets, [g[0] for g in groups], mode=mode, n_pre=n_pre, split_classes=split_classes,
                       vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa, device=device)
@@ -233,6 +250,8 @@ def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (
             plan.upload_group(k, g[1], g[2], g[3], g[4])
         if vb is not None:
             plan.set_vb(vb)
+        if temp is not None:
+            plan.upload_temp(temp, cold_T)
         stats = plan.run()
         res = plan.download()
         res.stats = stats
@@ -247,8 +266,6 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence
     """One halo.  pre / post: sequences of (mass, x, y, z) fixed source groups summed before /
     after the members (same keywords as oracle.unbind_halo)."""
     n = len(x)
-    if split_classes and len(pre):
-        raise ValueError("split_classes (gas layout) sums the members first: use post=")
     ext = list(pre) + list(post)
     groups = [(np.array([0, len(g[0])], np.int64), g[0], g[1], g[2], g[3]) for g in ext]
     res = unbind_catalogue(np.array([0, n], np.int64), x, y, z, vx, vy, vz, mass, groups=groups,

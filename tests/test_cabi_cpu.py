@@ -21,7 +21,7 @@ def declared_symbols():
 def test_header_symbols_are_exported():
     L = _lib.lib()
     names = declared_symbols()
-    assert len(names) >= 18
+    assert len(names) >= 19
     for n in names:
         assert hasattr(L, n), "libhalma_unbind.so does not export %s" % n
     assert set(names) == set(_lib.EXPORTS)
@@ -29,7 +29,7 @@ def test_header_symbols_are_exported():
 
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.UnbindConfig) == 64
-    assert ctypes.sizeof(_lib.HaloResult) == 80
+    assert ctypes.sizeof(_lib.HaloResult) == 120
     assert ctypes.sizeof(_lib.RunStats) == 40
 
 

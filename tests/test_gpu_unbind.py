@@ -277,14 +277,52 @@ def test_rps_golden_fast(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", ["rps_one_dm", "rps_two_dm", "rps_sampled"])
-def test_most_bound_golden_exact(golden_dir, name):
+@pytest.mark.parametrize("fused", [True, False])
+def test_most_bound_golden_exact(golden_dir, name, fused):
     g = load(golden_dir, name)
     np.random.seed(int(g["np_seed"]))
     oripa = np.arange(len(g["st_x"])) + 1000
     out = halo_gas.most_bound_particle(g["gas_x"], g["gas_y"], g["gas_z"], g["gas_mass"], g["dm_x"], g["dm_y"],
                                        g["dm_z"], g["dm_mass"], g["st_x"], g["st_y"], g["st_z"], g["st_mass"],
-                                       oripa, int(g["lim"]), float(g["mass_dm_part"]), mode="exact")
+                                       oripa, int(g["lim"]), float(g["mass_dm_part"]), mode="exact", fused=fused)
     np.testing.assert_array_equal(np.array(out, dtype=np.float64), g["mb_out"])
+
+
+def test_most_bound_fused_large_matches_oracle_argmin():
+    # device-side arg-max of the potential (lowest index on ties) == np.argmin(-be) of the oracle
+    s, g, d = case(20000, 8000, 1500, extra=8)
+    oripa = np.arange(len(s)) + 7
+    for mode, variant in (("exact", "f32seq"), ("fast", "f64acc")):
+        out = halo_gas.most_bound_particle(g.x, g.y, g.z, g.mass, d.x, d.y, d.z, d.mass, s.x, s.y, s.z, s.mass,
+                                           oripa, 10 ** 9, 8e7, mode=mode)
+        be = O.most_bound_potential(g.x, g.y, g.z, g.mass, d.x, d.y, d.z, d.mass, s.x, s.y, s.z, s.mass, 10 ** 9,
+                                    8e7, variant=variant)
+        k = int(np.argmin(-be))
+        if mode == "exact":
+            assert out[3] == oripa[k]
+        else:
+            kk = int(out[3] - 7)          # fast: the winner must be within rounding of the oracle's minimum
+            assert abs(be[kk] / be[k] - 1) < 1e-6
+
+
+def test_rps_mass_sums_on_device(golden_dir):
+    g = load(golden_dir, "rps_two_dm")
+    ext = [(g["dm_mass"], g["dm_x"], g["dm_y"], g["dm_z"]), (g["st_mass"], g["st_x"], g["st_y"], g["st_z"])]
+    n = len(g["gas_x"])
+    groups = [(np.array([0, len(e[0])], np.int64),) + e for e in ext]
+    for max_iter in (1, 64):
+        res = unbind_catalogue(np.array([0, n], np.int64), g["gas_x"], g["gas_y"], g["gas_z"], g["gas_vx"], g["gas_vy"],
+                               g["gas_vz"], g["gas_mass"], groups=groups, split_classes=True, vb=g["vb"].reshape(1, 3),
+                               kappa=2.0, max_iter=max_iter, mode="exact", temp=g["gas_temp"])
+        h = res.halos[0]
+        bound = res.mask.astype(bool)
+        cold = g["gas_temp"] < 5e4
+        m = g["gas_mass"]
+        np.testing.assert_allclose(h.mass_initial, m.sum(), rtol=1e-13)
+        np.testing.assert_allclose(h.cold_bound_mass, m[cold & bound].sum(), rtol=1e-12)
+        np.testing.assert_allclose(h.unbound_cold_mass, m[cold & ~bound].sum(), rtol=1e-12)
+        np.testing.assert_allclose(h.unbound_hot_mass, m[~cold & ~bound].sum(), rtol=1e-12)
+        assert 0 <= h.most_bound < n and res.be32[h.most_bound] == res.be32[bound | ~bound].max() or max_iter > 1
 
 
 def test_stellar_onepass_golden(golden_dir):
