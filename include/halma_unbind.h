@@ -125,7 +125,11 @@ typedef struct halma_unbind_config {
     double  kappa;           /* factor_v**2 (stars) or 2.0 (gas); cast to float32        */
     int32_t rank;            /* split mode: this process's rank ...                      */
     int32_t n_ranks;         /* ... of n_ranks sharing ONE halo by target groups (1 = off) */
-    int32_t use_graph;       /* 1: run the loop as a CUDA graph with a device-side WHILE  */
+    int32_t use_graph;       /* 1: run the loop as ONE CUDA-graph launch (WHILE conditional node,
+                                condition set on the device by the scheduling kernel).  0: the host
+                                enqueues passes ahead of the device and learns about convergence from
+                                a pinned flag; gives per-launch CUDA-event timing in halma_run_stats.
+                                Ignored (0) in split mode.                                   */
     int32_t reserved;
 } halma_unbind_config;
 
@@ -148,7 +152,8 @@ typedef struct halma_halo_result {
 
 typedef struct halma_run_stats {
     double  total_ms;        /* CUDA-event time of the whole run on the plan's stream    */
-    double  potential_ms;    /* sum over potential-kernel launches (CUDA events)         */
+    double  potential_ms;    /* sum over potential-kernel launches (CUDA events); 0 with
+                                use_graph = 1, where single launches cannot be timed      */
     int32_t potential_launches;
     int32_t launches;        /* all kernel launches issued by the run                    */
     int32_t passes;          /* loop passes executed (max over haloes)                   */

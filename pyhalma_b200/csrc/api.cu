@@ -443,6 +443,10 @@ struct halma_plan {
     DBuf<double> d_hrps, d_temp;
     bool temp_up = false;
     double cold_T = 5e4;
+    // CUDA-graph loop driver (cfg.use_graph): one graph launch runs every pass
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    bool graph_dirty = true;
     DBuf<uint8_t> d_flag, d_mask;
     DBuf<float> d_be;
     DBuf<double> d_E;
@@ -484,6 +488,8 @@ struct halma_plan {
     }
     ~halma_plan()
     {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (graph) cudaGraphDestroy(graph);
         free_buffers();                       // stream-ordered frees, before the stream goes away
         if (stream) cudaStreamSynchronize(stream);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
@@ -921,6 +927,7 @@ extern "C" int halma_plan_upload_temp(halma_plan *P, const double *temp, double 
     P->cold_T = cold_T;
     P->lp.temp = P->d_temp.p;
     P->lp.cold_T = cold_T;
+    P->graph_dirty = true;          // kernel parameters are baked into the graph
     return HALMA_OK;
 }
 
@@ -944,6 +951,62 @@ extern "C" int halma_plan_join(halma_plan *P, const void *unique_id_128)
     memcpy(&id, unique_id_128, sizeof id);
     int e = g_nccl.CommInitRank(&P->comm, P->cfg.n_ranks, id, P->cfg.rank);
     return e ? nccl_fail(e, "ncclCommInitRank") : HALMA_OK;
+}
+
+// Kernels of one pass, without events or host copies (shared by both loop drivers).
+static int enqueue_pass_kernels(halma_plan *P, const LoopParams &lp)
+{
+    cudaStream_t s = P->stream;
+    const int sm = P->ctx->sm_count;
+    const int grid = sm * P->ctx->bps[P->cfg.mode];
+    CU_TRY(potential_launch(P->pp, P->cfg.mode, grid, s));
+    if (P->np) {
+        PotParams redo = P->pp;
+        redo.redo_only = 1;
+        CU_TRY(potential_launch(redo, P->cfg.mode, grid, s));
+    }
+    CU_TRY(launch_energy_flag(lp, sm, s));
+    CU_TRY(launch_halo_decide(lp, 0, sm, s));
+    CU_TRY(launch_compact(lp, sm, s));
+    CU_TRY(launch_schedule(lp, 0, s));
+    return HALMA_OK;
+}
+
+// Device-resident loop as a CUDA graph: a WHILE conditional node whose body is one pass;
+// k_schedule sets the condition on the device (any halo still active), so one graph launch
+// runs the whole unbinding without the host.
+static int plan_build_graph(halma_plan *P)
+{
+    if (P->gexec) {
+        cudaGraphExecDestroy(P->gexec);
+        P->gexec = nullptr;
+    }
+    if (P->graph) {
+        cudaGraphDestroy(P->graph);
+        P->graph = nullptr;
+    }
+    CU_TRY(cudaGraphCreate(&P->graph, 0));
+    cudaGraphConditionalHandle handle;
+    CU_TRY(cudaGraphConditionalHandleCreate(&handle, P->graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp = {};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t node;
+    CU_TRY(cudaGraphAddNode(&node, P->graph, nullptr, 0, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    LoopParams lp = P->lp;
+    lp.cond_handle = handle;
+    CU_TRY(cudaStreamBeginCaptureToGraph(P->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_pass_kernels(P, lp);
+    cudaGraph_t captured = nullptr;
+    cudaError_t e = cudaStreamEndCapture(P->stream, &captured);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(HALMA_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+    CU_TRY(cudaGraphInstantiate(&P->gexec, P->graph, 0));
+    P->graph_dirty = false;
+    return HALMA_OK;
 }
 
 static int enqueue_pass(halma_plan *P, int pass)
@@ -997,6 +1060,7 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
     const size_t NU = static_cast<size_t>(P->n_user);
     const int nh = static_cast<int>(P->n_halo);
     int launches = 0, pot_launches = 0, passes = 0;
+    bool graph_run = false;
 
     CU_TRY(cudaEventRecord(P->ev_start, s));
     CU_TRY(cudaMemsetAsync(P->d_st.p, 0, sizeof(LoopState), s));
@@ -1020,6 +1084,19 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         const int max_iter = P->cfg.max_iter;
         int queued = 0;
         bool done = false;
+        graph_run = P->cfg.use_graph && P->cfg.n_ranks == 1;
+        if (graph_run) {
+            // graph driver: every pass inside one launch, convergence decided on the device
+            if (P->graph_dirty)
+                if (int rc = plan_build_graph(P)) return rc;
+            CU_TRY(cudaGraphLaunch(P->gexec, s));
+            LoopState hst;
+            CU_TRY(cudaMemcpyAsync(&hst, P->d_st.p, sizeof hst, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            passes = hst.pass;
+            queued = passes;        // kernels of the early-out pass that ends the loop are not counted
+            done = true;
+        }
         while (!done) {
             while (queued < max_iter && queued < passes + kAhead) {
                 if (int rc = enqueue_pass(P, queued)) return rc;
@@ -1044,8 +1121,8 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, P->ev_start, P->ev_stop));
         stats->total_ms = ms;
-        double pot = 0.0;
-        for (int k = 0; k < pot_launches; ++k) {
+        double pot = 0.0;      // per-launch events exist only with the enqueue-ahead driver
+        for (int k = 0; k < pot_launches && !graph_run; ++k) {
             CU_TRY(cudaEventElapsedTime(&ms, P->ev[3 * k], P->ev[3 * k + 1]));
             pot += ms;
         }

@@ -404,7 +404,11 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
     __shared__ int sred[33];
     __shared__ int s_total_groups, s_carry, s_any;
     LoopState *st = p.st;
-    if (!init && !st->any_active) return;
+    if (!init && !st->any_active) {
+        // graph driver: nothing left to do, leave the WHILE node
+        if (threadIdx.x == 0 && p.cond_handle) cudaGraphSetConditional(p.cond_handle, 0u);
+        return;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // commit
     int groups = 0, any = 0;
@@ -503,6 +507,8 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
             st->parity ^= 1;
             st->pass += 1;
         }
+        // graph driver: run another pass of the WHILE body iff some halo is still active
+        if (p.cond_handle) cudaGraphSetConditional(p.cond_handle, s_any ? 1u : 0u);
     }
     for (int o = 16; o > 0; o >>= 1) max_split = max(max_split, __shfl_down_sync(0xffffffffu, max_split, o));
     if (lane == 0 && max_split > 1) atomicMax(&st->n_split, max_split);

@@ -52,6 +52,8 @@ struct LoopParams {
     SortedAxis ax[3];
     int32_t *halo_redo;
     int32_t np_enabled;
+    // CUDA-graph loop driver: conditional handle of the WHILE node (0 = not in a graph)
+    unsigned long long cond_handle;
 };
 
 cudaError_t launch_pack_members(const LoopParams &p, int sm_count, cudaStream_t s);

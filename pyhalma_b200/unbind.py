@@ -103,7 +103,8 @@ class UnbindPlan:
 
     def __init__(self, offsets, ext_offsets: Sequence = (), *, mode="fast", n_pre: int = 0,
                  split_classes: bool = False, vb_fixed: bool = False, max_iter: int = 64,
-                 G: float = G_CONST, kappa: float = 9.0, device: int = 0, rank: int = 0, n_ranks: int = 1):
+                 G: float = G_CONST, kappa: float = 9.0, device: int = 0, rank: int = 0, n_ranks: int = 1,
+                 use_graph: Optional[bool] = None):
         L = _lib.lib()
         self._L = L
         self.offsets = _i64(offsets)
@@ -130,6 +131,10 @@ class UnbindPlan:
         cfg.kappa = float(kappa)
         cfg.rank = rank
         cfg.n_ranks = n_ranks
+        if use_graph is None:
+            import os
+            use_graph = os.environ.get("HALMA_GRAPH", "0") not in ("0", "")
+        cfg.use_graph = int(bool(use_graph))
         self.cfg = cfg
         ptrs = (C.POINTER(C.c_int64) * max(1, len(self.ext_offsets)))()
         for g, e in enumerate(self.ext_offsets):

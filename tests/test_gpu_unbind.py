@@ -232,6 +232,39 @@ def test_idempotence_and_rerun():
     assert again.n_iter == 1 and again.mask.all()
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_graph_loop_driver_matches_enqueue_driver(mode):
+    # use_graph=1: the whole loop is one CUDA-graph launch with a device-side WHILE node
+    off, cols = ragged_catalogue()
+    out = []
+    for use_graph in (False, True):
+        with UnbindPlan(off, mode=mode, kappa=1.0, use_graph=use_graph) as plan:
+            plan.upload_members(*cols)
+            st = plan.run()
+            res = plan.download()
+            st2 = plan.run()                     # re-launch of the instantiated graph
+            res2 = plan.download()
+        assert np.array_equal(res.mask, res2.mask) and st.passes == st2.passes
+        out.append((st, res))
+    (sa, a), (sb, b) = out
+    assert sa.passes == sb.passes and sa.pairs == sb.pairs
+    assert np.array_equal(a.mask, b.mask) and np.array_equal(a.be32, b.be32) and np.array_equal(a.energy, b.energy)
+    assert np.array_equal(a.idx_packed, b.idx_packed)
+    assert [h.n_iter for h in a.halos] == [h.n_iter for h in b.halos]
+    # a large single halo through the predicate-free kernel inside the graph
+    s, g, d = case(40000, 90000, 1000, extra=9)
+    kw = dict(pre=[g.pos_mass()], post=[d.pos_mass()], kappa=9.0, mode=mode)
+    if mode == "fast":
+        r0 = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, **kw)
+        import os
+        os.environ["HALMA_GRAPH"] = "1"
+        try:
+            r1 = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, **kw)
+        finally:
+            os.environ.pop("HALMA_GRAPH")
+        assert np.array_equal(r0.mask, r1.mask) and np.array_equal(r0.be32, r1.be32) and r0.n_iter == r1.n_iter
+
+
 def test_degenerate_inputs():
     r = unbind_halo([], [], [], [], [], [], [], mode="exact")
     assert r.n_iter == 0 and r.mass == 0.0 and r.vb == (0., 0., 0.) and len(r.idx) == 0
