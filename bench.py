@@ -100,21 +100,29 @@ def make_workload(name: str, rank: int, world: int = 1):
     raise SystemExit("unknown workload %r" % name)
 
 
-_UID_CACHE = {}
+_COMM = {}
+
+
+def shared_comm(rank, world, device):
+    """One NCCL communicator per process for all split-mode plans."""
+    if "c" not in _COMM:
+        import torch.distributed as dist
+        from pyhalma_b200.unbind import Communicator, nccl_unique_id
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        _COMM["c"] = Communicator(uid[0], rank, world, device)
+    return _COMM["c"]
 
 
 def make_plan(job, mode, device, rank=0, world=1, upload=True):
-    from pyhalma_b200.unbind import UnbindPlan, nccl_unique_id
+    from pyhalma_b200.unbind import UnbindPlan
     kw = job["kw"]
     split = job["split"] and world > 1
     plan = UnbindPlan(job["offsets"], [g[0] for g in job["groups"]], mode=mode, n_pre=kw["n_pre"],
                       split_classes=kw["split_classes"], vb_fixed=kw["vb"] is not None, max_iter=64,
                       kappa=kw["kappa"], device=device, rank=rank if split else 0, n_ranks=world if split else 1)
     if split:
-        import torch.distributed as dist
-        uid = [nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        plan.join(uid[0])
+        plan.use_comm(shared_comm(rank, world, device))
     if upload:
         upload_job(plan, job)
     return plan
@@ -402,6 +410,8 @@ def run_gpu(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     for p in plans:
         p.close()
+    if "c" in _COMM:
+        _COMM.pop("c").close()
     if world > 1:
         dist.destroy_process_group()
 

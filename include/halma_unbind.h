@@ -184,6 +184,13 @@ int halma_plan_set_vb(halma_plan *plan, const double *vb);
  * made by rank 0 (halma_nccl_unique_id) and broadcast by the caller. */
 int halma_nccl_unique_id(void *unique_id_128);
 int halma_plan_join(halma_plan *plan, const void *unique_id_128);
+/* A communicator that outlives plans (creating one costs ~0.1 s): create it once per
+ * process, hand it to every split-mode plan with halma_plan_use_comm (the plan does not
+ * own it), destroy it after the last plan. */
+typedef struct halma_comm halma_comm;
+int halma_comm_create(int device, int rank, int n_ranks, const void *unique_id_128, halma_comm **out);
+void halma_comm_destroy(halma_comm *comm);
+int halma_plan_use_comm(halma_plan *plan, halma_comm *comm);
 
 /* Runs the whole loop on the device from the uploaded (pristine) inputs; can be called
  * repeatedly.  Blocks until done; stats may be null. */

@@ -21,7 +21,7 @@ EXPORTS = (
     "halma_last_error", "halma_abi_version", "halma_device_count", "halma_device_info",
     "halma_host_alloc", "halma_host_free", "halma_potential_f32", "halma_potential_workspace_bytes",
     "halma_potential_f32_dev", "halma_plan_create", "halma_plan_destroy", "halma_plan_upload_members",
-    "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join",
+    "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join", "halma_comm_create", "halma_comm_destroy", "halma_plan_use_comm",
     "halma_plan_run", "halma_plan_download", "halma_unbind_halo", "halma_microbench",
 )
 
@@ -89,12 +89,17 @@ def lib() -> C.CDLL:
     L.halma_plan_set_vb.argtypes = [vp, vp]
     L.halma_nccl_unique_id.argtypes = [vp]
     L.halma_plan_join.argtypes = [vp, vp]
+    L.halma_comm_create.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]
+    L.halma_comm_destroy.argtypes = [vp]
+    L.halma_comm_destroy.restype = None
+    L.halma_plan_use_comm.argtypes = [vp, vp]
     L.halma_plan_run.argtypes = [vp, C.POINTER(RunStats)]
     L.halma_plan_download.argtypes = [vp, vp, vp, vp, vp, C.POINTER(HaloResult)]
     L.halma_microbench.argtypes = [i32, f64p]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("halma_last_error", "halma_potential_workspace_bytes", "halma_plan_destroy"):
+        if name not in ("halma_last_error", "halma_potential_workspace_bytes", "halma_plan_destroy",
+                        "halma_comm_destroy"):
             fn.restype = i32
     if L.halma_abi_version() != 1:
         raise ImportError("libhalma_unbind ABI version mismatch")

@@ -457,6 +457,7 @@ struct halma_plan {
     std::vector<cudaEvent_t> ev;          // per pass: before K1, after K1, end of pass
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     void *comm = nullptr;                 // ncclComm_t (split mode)
+    bool comm_owned = false;
     bool ran = false;
     // predicate-free FAST path: sorted source copies (sortprep.cu)
     bool np = false, sorted_dirty = true;
@@ -492,7 +493,7 @@ struct halma_plan {
         if (graph) cudaGraphDestroy(graph);
         free_buffers();                       // stream-ordered frees, before the stream goes away
         if (stream) cudaStreamSynchronize(stream);
-        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        if (comm && comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         for (auto e : ev) cudaEventDestroy(e);
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_stop) cudaEventDestroy(ev_stop);
@@ -950,7 +951,55 @@ extern "C" int halma_plan_join(halma_plan *P, const void *unique_id_128)
     UID128 id;
     memcpy(&id, unique_id_128, sizeof id);
     int e = g_nccl.CommInitRank(&P->comm, P->cfg.n_ranks, id, P->cfg.rank);
-    return e ? nccl_fail(e, "ncclCommInitRank") : HALMA_OK;
+    if (e) return nccl_fail(e, "ncclCommInitRank");
+    P->comm_owned = true;
+    return HALMA_OK;
+}
+
+struct halma_comm {
+    void *nccl = nullptr;
+    int device = 0, rank = 0, n_ranks = 1;
+};
+
+extern "C" int halma_comm_create(int device, int rank, int n_ranks, const void *unique_id_128, halma_comm **out)
+{
+    if (!unique_id_128 || !out) return fail(HALMA_ERR_INVALID, "null pointer");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(HALMA_ERR_INVALID, "bad rank");
+    if (int rc = load_nccl()) return rc;
+    DeviceCtx *c;
+    if (int rc = get_ctx(device, &c)) return rc;
+    UID128 id;
+    memcpy(&id, unique_id_128, sizeof id);
+    halma_comm *C = new halma_comm();
+    C->device = device;
+    C->rank = rank;
+    C->n_ranks = n_ranks;
+    int e = g_nccl.CommInitRank(&C->nccl, n_ranks, id, rank);
+    if (e) {
+        delete C;
+        return nccl_fail(e, "ncclCommInitRank");
+    }
+    *out = C;
+    return HALMA_OK;
+}
+
+extern "C" void halma_comm_destroy(halma_comm *comm)
+{
+    if (!comm) return;
+    if (comm->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(comm->nccl);
+    delete comm;
+}
+
+extern "C" int halma_plan_use_comm(halma_plan *P, halma_comm *comm)
+{
+    if (!P || !comm) return fail(HALMA_ERR_INVALID, "null pointer");
+    if (P->cfg.n_ranks < 2) return fail(HALMA_ERR_STATE, "plan was not created in split mode");
+    if (comm->n_ranks != P->cfg.n_ranks || comm->rank != P->cfg.rank || comm->device != P->cfg.device)
+        return fail(HALMA_ERR_INVALID, "communicator does not match the plan's rank / n_ranks / device");
+    if (P->comm && P->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(P->comm);
+    P->comm = comm->nccl;
+    P->comm_owned = false;
+    return HALMA_OK;
 }
 
 // Kernels of one pass, without events or host copies (shared by both loop drivers).

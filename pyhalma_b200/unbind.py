@@ -202,6 +202,11 @@ class UnbindPlan:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _lib.check(self._L.halma_plan_join(self._h, buf))
 
+    def use_comm(self, comm: "Communicator"):
+        """Split mode with a communicator that outlives the plan."""
+        self._comm = comm
+        _lib.check(self._L.halma_plan_use_comm(self._h, comm._h))
+
     # -- execution ------------------------------------------------------------------------
     def run(self) -> RunStats:
         st = _lib.RunStats()
@@ -228,6 +233,32 @@ class UnbindPlan:
                                       float(r.mass_initial), float(r.cold_bound_mass),
                                       float(r.unbound_cold_mass), float(r.unbound_hot_mass)))
         return CatalogueResult(self.offsets, m, b, e, i, out)
+
+
+class Communicator:
+    """NCCL communicator shared by the split-mode plans of one process (creating one takes
+    ~0.1 s).  unique_id: the 128 bytes made by rank 0 with nccl_unique_id() and broadcast by
+    the caller (e.g. torch.distributed.broadcast_object_list)."""
+
+    def __init__(self, unique_id: bytes, rank: int, n_ranks: int, device: int = 0):
+        _lib.ensure_nccl_path()
+        self._L = _lib.lib()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        h = C.c_void_p()
+        _lib.check(self._L.halma_comm_create(device, rank, n_ranks, buf, C.byref(h)))
+        self._h = h
+        self.rank, self.n_ranks, self.device = rank, n_ranks, device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.halma_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def nccl_unique_id() -> bytes:

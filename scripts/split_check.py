@@ -10,12 +10,16 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from pyhalma_b200 import synth
-from pyhalma_b200.unbind import UnbindPlan, nccl_unique_id, unbind_halo
+from pyhalma_b200.unbind import Communicator, UnbindPlan, nccl_unique_id, unbind_halo
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
+uid0 = [nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid0, src=0)
+shared = Communicator(uid0[0], rank, world, local)          # reused by the last case
+case_no = 0
 for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000), ("fast", 90000, 40000)):
     c = synth.config1(n_star, n_gas, n_dm=500)
     s, g, d = c.stars, c.gas, c.dm
@@ -24,7 +28,11 @@ for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000), ("fas
     off = np.array([0, len(s)], np.int64)
     eoff = [np.array([0, len(g)], np.int64), np.array([0, len(d)], np.int64)]
     with UnbindPlan(off, eoff, mode=mode, n_pre=1, kappa=9.0, device=local, rank=rank, n_ranks=world) as plan:
-        plan.join(uid[0])
+        if case_no == 2:
+            plan.use_comm(shared)
+        else:
+            plan.join(uid[0])
+        case_no += 1
         plan.upload_members(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass)
         plan.upload_group(0, g.mass, g.x, g.y, g.z)
         plan.upload_group(1, d.mass, d.x, d.y, d.z)
@@ -43,5 +51,6 @@ for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000), ("fas
             mode, len(s), res.halos[0].n_iter, res.halos[0].n_bound, bool(flag.item()), st.total_ms,
             single.stats.total_ms), flush=True)
     ok = ok and bool(flag.item())
+shared.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

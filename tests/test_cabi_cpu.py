@@ -21,7 +21,7 @@ def declared_symbols():
 def test_header_symbols_are_exported():
     L = _lib.lib()
     names = declared_symbols()
-    assert len(names) >= 19
+    assert len(names) >= 22
     for n in names:
         assert hasattr(L, n), "libhalma_unbind.so does not export %s" % n
     assert set(names) == set(_lib.EXPORTS)
