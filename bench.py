@@ -424,8 +424,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--cpu-targets", type=int, default=12000, help="targets per job in the cpu_baseline sample")
-    ap.add_argument("--ref-targets", type=int, default=2500, help="targets per job per step of --impl reference")
+    ap.add_argument("--cpu-targets", type=int, default=60000, help="targets per job in the cpu_baseline sample")
+    ap.add_argument("--ref-targets", type=int, default=20000, help="targets per job per step of --impl reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
