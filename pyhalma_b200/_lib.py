@@ -139,6 +139,55 @@ def microbench(device: int = 0) -> dict:
             "ffma2_gops": out[7]}
 
 
+class _PinnedBlock:
+    """Page-locked host block exposing the array interface; goes back to the pool when the
+    last numpy view of it dies."""
+
+    def __init__(self, ptr: int, size: int, nbytes: int, dtype, count: int):
+        self.ptr, self.size = ptr, size
+        import numpy as np
+        self.__array_interface__ = {"data": (ptr, False), "shape": (count,), "typestr": np.dtype(dtype).str,
+                                    "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_release(self.ptr, self.size)
+        except Exception:
+            pass
+
+
+_PINNED_FREE: dict = {}
+_PINNED_CACHED = [0]
+_PINNED_CACHE_LIMIT = 8 << 30
+
+
+def _pinned_release(ptr: int, size: int) -> None:
+    if _lib is None:
+        return
+    if _PINNED_CACHED[0] + size <= _PINNED_CACHE_LIMIT:
+        _PINNED_FREE.setdefault(size, []).append(ptr)
+        _PINNED_CACHED[0] += size
+    else:
+        _lib.halma_host_free(C.c_void_p(ptr))
+
+
+def pinned_empty(count: int, dtype):
+    """numpy array in page-locked host memory from a size-bucketed pool (cudaMallocHost costs
+    ~0.3 ms/MB, so result buffers are recycled).  Contents are uninitialised."""
+    import numpy as np
+    nbytes = max(int(count) * np.dtype(dtype).itemsize, 8)
+    size = 1 << (nbytes - 1).bit_length() if nbytes < (1 << 20) else ((nbytes + (1 << 20) - 1) >> 20) << 20
+    free = _PINNED_FREE.get(size)
+    if free:
+        ptr = free.pop()
+        _PINNED_CACHED[0] -= size
+    else:
+        p = C.c_void_p()
+        check(lib().halma_host_alloc(C.byref(p), size))
+        ptr = p.value
+    return np.asarray(_PinnedBlock(ptr, size, nbytes, dtype, int(count)))
+
+
 def ensure_nccl_path() -> None:
     """Point libhalma_unbind at the NCCL build torch ships (split mode only).  Found without
     importing torch; an explicit HALMA_NCCL_LIB wins."""

@@ -216,10 +216,11 @@ class UnbindPlan:
 
     def download(self, mask=True, be=True, energy=True, idx=True, halos=True) -> CatalogueResult:
         n = self.n
-        m = np.zeros(n, np.uint8) if mask else None
-        b = np.zeros(n, np.float32) if be else None
-        e = np.zeros(n, np.float64) if energy else None
-        i = np.zeros(n, np.int32) if idx else None
+        # result arrays live in pooled page-locked memory: D2H at link speed, no page faults
+        m = _lib.pinned_empty(n, np.uint8) if mask else None
+        b = _lib.pinned_empty(n, np.float32) if be else None
+        e = _lib.pinned_empty(n, np.float64) if energy else None
+        i = _lib.pinned_empty(n, np.int32) if idx else None
         hr = (_lib.HaloResult * max(1, self.n_halo))() if halos else None
         _lib.check(self._L.halma_plan_download(
             self._h, m.ctypes.data if mask else None, b.ctypes.data if be else None,

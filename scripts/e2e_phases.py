@@ -4,7 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
 
-jobs, desc, _ = bench.make_workload("cfg2", 0, 1)
+import sys as _s
+wl = _s.argv[1] if len(_s.argv) > 1 else "cfg2"
+jobs, desc, _ = bench.make_workload(wl, 0, 1)
 jobs = [dict(j, members=tuple(bench.pinned_copy(a) for a in j["members"]),
              groups=[(g[0],) + tuple(bench.pinned_copy(a) for a in g[1:]) for g in j["groups"]]) for j in jobs]
 for rep in range(4):

@@ -445,3 +445,71 @@ def test_cfg3_full_catalogue_properties_and_sampled_parity():
             assert res.halos[h].n_iter == o.n_iter
             np.testing.assert_allclose(res.halos[h].mass, o.mass, rtol=1e-12)
             np.testing.assert_allclose(res.halos[h].vb, o.vb, rtol=1e-6, atol=1e-9)
+
+
+# ---- error behaviour and odd inputs ---------------------------------------------------------
+def test_call_order_and_argument_errors():
+    from pyhalma_b200 import _lib
+    off = np.array([0, 10], np.int64)
+    x = np.arange(10.0)
+    with UnbindPlan(off, [np.array([0, 3], np.int64)], vb_fixed=True) as plan:
+        with pytest.raises(_lib.HalmaError) as e:
+            plan.run()
+        assert e.value.code == _lib.ERR_STATE                      # members not uploaded
+        plan.upload_members(x, x, x, x, x, x, x)
+        with pytest.raises(_lib.HalmaError) as e:
+            plan.run()
+        assert e.value.code == _lib.ERR_STATE                      # group 0 not uploaded
+        plan.upload_group(0, x[:3], x[:3], x[:3], x[:3])
+        with pytest.raises(_lib.HalmaError) as e:
+            plan.run()
+        assert e.value.code == _lib.ERR_STATE                      # vb_fixed without set_vb
+        with pytest.raises(_lib.HalmaError):
+            plan.download()                                         # nothing ran yet
+        with pytest.raises(ValueError):
+            plan.upload_members(x[:5], x, x, x, x, x, x)
+        with pytest.raises(ValueError):
+            plan.upload_group(0, x, x, x, x)
+        plan.set_vb([0., 0., 0.])
+        plan.run()
+        assert plan.download().halos[0].n_iter >= 1
+    with pytest.raises(_lib.HalmaError):
+        UnbindPlan(off, max_iter=0)
+    with pytest.raises(_lib.HalmaError):
+        UnbindPlan(np.array([0, 5, 3], np.int64))                   # decreasing offsets
+    with pytest.raises(ValueError):
+        UnbindPlan(off, mode="quick")
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_zero_mass_and_nan_members(mode):
+    rng = np.random.default_rng(21)
+    p = synth.plummer_stars(900, 2e-3, 1e6, rng, centre=(1.0, 2.0, 3.0))
+    p.mass[::7] = 0.0                                   # massless tracers: targets but no sources
+    variant = "f32seq" if mode == "exact" else "f64acc"
+    o = O.unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, kappa=9.0, variant=variant)
+    r = unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, kappa=9.0, mode=mode)
+    diff = r.mask != o.mask
+    assert np.all(O.energy_margin(o.energy, o.be32, 9.0)[diff] < (0 if mode == "exact" else BAND) + 1e-300)
+    np.testing.assert_allclose(r.mass, o.mass, rtol=1e-12)
+    # a NaN coordinate poisons every potential that sees it (reference: NaN /= x is true);
+    # NaN energies are neither bound nor unbound, so those particles drop out
+    q = synth.plummer_stars(300, 2e-3, 1e6, rng)
+    q.x[17] = np.nan
+    o = O.unbind_halo(q.x, q.y, q.z, q.vx, q.vy, q.vz, q.mass, kappa=9.0, variant=variant, max_iter=1)
+    r = unbind_halo(q.x, q.y, q.z, q.vx, q.vy, q.vz, q.mass, kappa=9.0, mode=mode, max_iter=1)
+    assert np.array_equal(np.isnan(r.be32), np.isnan(o.be32))
+    # (a particle sharing a float32 coordinate with the NaN one never sees it, so a few stay finite)
+    assert np.array_equal(r.mask, o.mask) and r.mask.sum() <= 3
+
+
+def test_catalogue_fixed_bulk_velocity_per_halo():
+    off, cols = ragged_catalogue()
+    nh = len(off) - 1
+    vb = np.random.default_rng(4).normal(0, 50, (nh, 3))
+    res = unbind_catalogue(off, *cols, kappa=2.0, vb=vb, mode="exact")
+    for h in (3, 9, 15, 19):
+        a, b = off[h], off[h + 1]
+        o = O.unbind_halo(*[c[a:b] for c in cols], kappa=2.0, vb_fixed=vb[h])
+        assert np.array_equal(res.halo_mask(h), o.mask) and res.halos[h].n_iter == o.n_iter
+        assert res.halos[h].vb == tuple(vb[h])
