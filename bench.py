@@ -367,7 +367,8 @@ def run_gpu(args, rank, local_rank, world):
         peak = mb["rsq_per_clk_sm"] * mb["sm_count"] * sm_mhz * 1e6 / 1e9
         n_src = [len(j["members"][0]) + sum(len(g[1]) for g in j["groups"]) for j in jobs]
         n_tgt = [len(j["members"][0]) for j in jobs]
-        alg_bytes_first_pass = sum(16 * s + 12 * t_ + 8 * t_ for s, t_ in zip(n_src, n_tgt))
+        # predicate-free path: sources are read once by the main tickets and once per axis-sorted copy
+        alg_bytes_first_pass = sum(16 * s * 4 + 20 * t_ + 24 * t_ for s, t_ in zip(n_src, n_tgt))
         roofline = {
             "bound": "mufu", "kernel": "k_potential_fast" if mode == "fast" else "k_potential_exact",
             "achieved": pot_rate, "peak": peak, "unit": UNIT, "frac": pot_rate / peak,
@@ -383,6 +384,15 @@ def run_gpu(args, rank, local_rank, world):
             "traffic": None,
             "microbench": mb,
         }
+        try:
+            # DRAM bytes per launch of the same kernel at this workload's first pass, from the
+            # committed `ncu --set full` capture (profiles/ncu_traffic_r01.json)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+            if tr.get("workload") == args.workload:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_note"] = tr["note"]
+        except Exception:
+            pass
         if world == 1:
             cp, cs, threads = cpu_sample(jobs, args.cpu_targets)
             cpu = {"value": cp / cs / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
