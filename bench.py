@@ -97,6 +97,20 @@ def make_workload(name: str, rank: int, world: int = 1):
         jobs = [dict(kind="giant", offsets=single(n), members=(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass), groups=[],
                      split=world > 1, kw=dict(n_pre=0, split_classes=False, vb=None, kappa=9.0))]
         return jobs, desc, "strong"
+    if name == "cfg5":
+        scale = float(os.environ.get("HALMA_CFG5_SCALE", "1.0"))
+        case = synth.config5(int(1e7 * scale), int(2e6 * scale), int(5e5 * scale))    # the same on every rank
+        s, g, d = case.stars, case.gas, case.dm
+        M = float(np.sum(s.mass))
+        vb = np.array([np.sum(s.mass * s.vx), np.sum(s.mass * s.vy), np.sum(s.mass * s.vz)]) / M
+        desc = {"workload": "cfg5: cluster gas unbinding, %d lattice gas cells against themselves + %d stars + %d DM "
+                            "particles, targets split over the GPUs, all-reduce of potentials and corrections per pass"
+                            % (len(g), len(s), len(d)), "n_gas": len(g), "n_star": len(s), "n_dm": len(d),
+                "parallelism": "target groups round-robin over %d GPU(s), sources replicated" % world}
+        jobs = [dict(kind="cluster-gas", offsets=single(len(g)), members=(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass),
+                     groups=[(single(len(d)), d.mass, d.x, d.y, d.z), (single(len(s)), s.mass, s.x, s.y, s.z)],
+                     split=world > 1, kw=dict(n_pre=0, split_classes=True, vb=vb, kappa=2.0))]
+        return jobs, desc, "strong"
     raise SystemExit("unknown workload %r" % name)
 
 

@@ -1064,6 +1064,8 @@ static int enqueue_pass(halma_plan *P, int pass)
     const int sm = P->ctx->sm_count;
     const int grid = sm * P->ctx->bps[P->cfg.mode];
     CU_TRY(cudaEventRecord(P->ev[3 * pass], s));
+    if (P->np && P->cfg.n_ranks > 1)      // split mode: every correction entry is written by one rank only
+        CU_TRY(cudaMemsetAsync(P->d_corr.p, 0, 3 * static_cast<size_t>(P->n_pad) * sizeof(double), s));
     CU_TRY(potential_launch(P->pp, P->cfg.mode, grid, s));
     if (P->np) {
         // haloes whose predicate-free sums came out non-finite are recomputed with the predicate
@@ -1073,6 +1075,9 @@ static int enqueue_pass(halma_plan *P, int pass)
                                      /*ncclMax*/ 2, P->comm, s);
             if (e) return nccl_fail(e, "ncclAllReduce(flags)");
             CU_TRY(launch_sync_redo(P->lp, s));
+            e = g_nccl.AllReduce(P->d_corr.p, P->d_corr.p, 3 * static_cast<size_t>(P->n_pad), /*ncclFloat64*/ 8,
+                                 /*ncclSum*/ 0, P->comm, s);
+            if (e) return nccl_fail(e, "ncclAllReduce(corrections)");
         }
         PotParams redo = P->pp;
         redo.redo_only = 1;

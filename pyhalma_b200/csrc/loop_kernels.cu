@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
                 max_split = max(max_split, S);
                 items = my_groups(n, p.group_size, p.rank, p.n_ranks) * S;
                 // correction tickets: three axes x blocks of the (static) sorted member list
-                if (p.np_enabled) items += 3 * ((p.halo[h].n0 + p.group_size - 1) / p.group_size);
+                if (p.np_enabled) items += 3 * my_groups(p.halo[h].n0, p.group_size, p.rank, p.n_ranks);
             }
         }
         // inclusive warp scan

@@ -166,7 +166,8 @@ struct Ticket {
 
 // Ticket layout of a halo (must match loop_kernels.cu::k_schedule):
 //   [0, mine * S)                    main tickets, s-major
-//   [mine * S, mine * S + 3 * nblk)  correction tickets (NP path), axis-major
+//   [mine * S, mine * S + 3 * myblk) correction tickets (NP path), axis-major; myblk = this rank's
+//                                    share of the ceil(n0 / group) blocks of the sorted member list
 template <int kGroup>
 __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Ticket &t)
 {
@@ -194,10 +195,12 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
     }
     if (!p.np_enabled) return false;
     local -= n_main;
+    // correction blocks are dealt round-robin to the ranks like the target groups
     const int nblk = (p.halo[t.h].n0 + kGroup - 1) / kGroup;
-    if (nblk <= 0 || local >= 3 * nblk) return false;
-    t.corr_axis = local / nblk;
-    t.group = local % nblk;
+    const int myblk = (nblk - p.rank + p.n_ranks - 1) / p.n_ranks;
+    if (myblk <= 0 || local >= 3 * myblk) return false;
+    t.corr_axis = local / myblk;
+    t.group = (local % myblk) * p.n_ranks + p.rank;
     t.s = 0;
     return true;
 }

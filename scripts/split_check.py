@@ -51,6 +51,33 @@ for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000), ("fas
             mode, len(s), res.halos[0].n_iter, res.halos[0].n_bound, bool(flag.item()), st.total_ms,
             single.stats.total_ms), flush=True)
     ok = ok and bool(flag.item())
+# gas layout on a lattice (dense coordinate sharing): correction tickets are distributed over
+# the ranks and their planes all-reduced
+c = synth.config1(30000, 60000, n_dm=800)
+s, g, d = c.stars, c.gas, c.dm
+M = s.mass.sum()
+vb = np.array([np.sum(s.mass * s.vx), np.sum(s.mass * s.vy), np.sum(s.mass * s.vz)]) / M
+off = np.array([0, len(g)], np.int64)
+eoff = [np.array([0, len(d)], np.int64), np.array([0, len(s)], np.int64)]
+with UnbindPlan(off, eoff, mode="fast", split_classes=True, vb_fixed=True, kappa=2.0, device=local, rank=rank,
+                n_ranks=world) as plan:
+    plan.use_comm(shared)
+    plan.upload_members(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass)
+    plan.upload_group(0, d.mass, d.x, d.y, d.z)
+    plan.upload_group(1, s.mass, s.x, s.y, s.z)
+    plan.set_vb(vb)
+    st = plan.run()
+    res = plan.download()
+single = unbind_halo(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass, post=[d.pos_mass(), s.pos_mass()], split_classes=True,
+                     kappa=2.0, vb_fixed=vb, mode="fast", device=local)
+same = (np.array_equal(res.mask.astype(bool), single.mask) and np.array_equal(res.be32.view(np.uint32), single.be32.view(np.uint32))
+        and np.array_equal(res.energy, single.energy) and res.halos[0].n_iter == single.n_iter)
+flag = torch.tensor([1 if same else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("split gas-lattice fast: n=%d passes=%d bound=%d identical_on_all_ranks=%s" % (
+        len(g), res.halos[0].n_iter, res.halos[0].n_bound, bool(flag.item())), flush=True)
+ok = ok and bool(flag.item())
 shared.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -20,4 +20,4 @@ def test_split_mode_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "split_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("identical_on_all_ranks=True") == 3
+    assert out.stdout.count("identical_on_all_ranks=True") == 4

@@ -89,3 +89,48 @@ def test_gather_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(results)
+
+
+def _split_worker(rank, world, port, q):
+    """Emulates the split-mode protocol of csrc/api.cu with the CPU oracle: every rank holds
+    the whole halo, evaluates only the target groups it owns, and the potentials are summed
+    over ranks (all-reduce).  Each element has exactly one non-zero contributor, so the sum
+    must equal the single-process result bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = synth.config1(1500, 700, n_dm=100)
+        s, g = c.stars, c.gas
+        src = [np.concatenate((getattr(g, k), getattr(s, k))) for k in ("mass", "x", "y", "z")]
+        own = sharding.split_owner(len(s), 128, world) == rank
+        phi = np.zeros(len(s), np.float64)
+        if own.any():
+            phi[own] = O.brute_force_binding_energy_fortran(*src, s.x[own], s.y[own], s.z[own], variant="f64acc")
+        t = torch.from_numpy(phi)
+        dist.all_reduce(t)
+        full = O.brute_force_binding_energy_fortran(*src, s.x, s.y, s.z, variant="f64acc")
+        q.put(bool(np.array_equal(t.numpy(), full)) and bool(own.sum() > 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_protocol_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(results)
