@@ -48,7 +48,9 @@ extern "C" int halma_abi_version(void) { return HALMA_ABI_VERSION; }
 struct DeviceCtx {
     bool ready = false;
     int sm_count = 0;
-    int bps[2] = {0, 0};          // resident potential blocks per SM, by mode
+    int bps_exact = 0;            // resident potential blocks per SM, EXACT kernel
+    int bps_fast[kMaxVariants] = {0};   // ... and per FAST kernel shape
+    int blocks(int mode, int variant) const { return mode == HALMA_MODE_EXACT ? bps_exact : bps_fast[variant]; }
     cudaStream_t stream = nullptr;
     // grow-only scratch of the host-pointer potential call
     void *scratch = nullptr;
@@ -79,8 +81,9 @@ static int get_ctx(int device, DeviceCtx **out)
         if (prop.major < 10)
             return fail(HALMA_ERR_NO_DEVICE, "device is not sm_100 or newer; this library is built for sm_100a only");
         c.sm_count = prop.multiProcessorCount;
-        CU_TRY(potential_configure(HALMA_MODE_FAST, &c.bps[HALMA_MODE_FAST]));
-        CU_TRY(potential_configure(HALMA_MODE_EXACT, &c.bps[HALMA_MODE_EXACT]));
+        CU_TRY(potential_configure(HALMA_MODE_EXACT, 0, &c.bps_exact));
+        for (int v = 0; v < potential_num_variants() && v < kMaxVariants; ++v)
+            CU_TRY(potential_configure(HALMA_MODE_FAST, v, &c.bps_fast[v]));
         CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         CU_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -231,8 +234,9 @@ static int potential_dev(DeviceCtx *c, int mode, const float *sm, const float *s
         CU_TRY(cudaMemsetAsync(out_be, 0, n_tgt * sizeof(float), stream));
         return HALMA_OK;
     }
-    const int group = potential_group_size(mode);
-    const int grid = c->sm_count * c->bps[mode];
+    const int variant = potential_pick_variant((n_tgt + 127) / 128, n_src, c->sm_count * c->bps_fast[0] * (kPotentialBlock / 32));
+    const int group = potential_group_size(mode, variant);
+    const int grid = c->sm_count * c->blocks(mode, variant);
     const int S = choose_split(mode, n_tgt, n_src, group, kNominalTickets);
     const int64_t groups = (n_tgt + group - 1) / group;
 
@@ -274,7 +278,7 @@ static int potential_dev(DeviceCtx *c, int mode, const float *sm, const float *s
     p.tgt_members = 0;
     p.rank = 0;
     p.n_ranks = 1;
-    CU_TRY(potential_launch(p, mode, grid, stream));
+    CU_TRY(potential_launch(p, mode, variant, grid, stream));
     const int fb = static_cast<int>(std::min<int64_t>((n_tgt + 255) / 256, c->sm_count * 8));
     k_fold_to_f32<<<fb, 256, 0, stream>>>(p.phi_part, p.phi_stride, S, n_tgt, out_be);
     CU_TRY(cudaGetLastError());
@@ -460,6 +464,7 @@ struct halma_plan {
     bool comm_owned = false;
     bool ran = false;
     // predicate-free FAST path: sorted source copies (sortprep.cu)
+    int variant = 0;                      // FAST kernel shape (potential.cu)
     bool np = false, sorted_dirty = true;
     int64_t n_spad = 0, n_valid = 0, n_tot = 0;
     int max_ext = 0;
@@ -749,7 +754,15 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.vb_fixed = cfg.vb_fixed;
     L.max_iter = cfg.max_iter;
     L.mode = cfg.mode;
-    L.group_size = potential_group_size(cfg.mode);
+    {
+        int64_t g128 = 0, max_src = 0;
+        for (int64_t h = 0; h < nh; ++h) {
+            g128 += (halo[h].n0 + 127) / 128;
+            max_src = std::max<int64_t>(max_src, static_cast<int64_t>(halo[h].n0) + halo[h].n_ext);
+        }
+        P->variant = potential_pick_variant(g128, max_src, P->ctx->sm_count * P->ctx->bps_fast[0] * (kPotentialBlock / 32));
+    }
+    L.group_size = potential_group_size(cfg.mode, P->variant);
     L.rank = cfg.rank;
     L.n_ranks = cfg.n_ranks;
     L.target_items = kNominalTickets;
@@ -1007,12 +1020,12 @@ static int enqueue_pass_kernels(halma_plan *P, const LoopParams &lp)
 {
     cudaStream_t s = P->stream;
     const int sm = P->ctx->sm_count;
-    const int grid = sm * P->ctx->bps[P->cfg.mode];
-    CU_TRY(potential_launch(P->pp, P->cfg.mode, grid, s));
+    const int grid = sm * P->ctx->blocks(P->cfg.mode, P->variant);
+    CU_TRY(potential_launch(P->pp, P->cfg.mode, P->variant, grid, s));
     if (P->np) {
         PotParams redo = P->pp;
         redo.redo_only = 1;
-        CU_TRY(potential_launch(redo, P->cfg.mode, grid, s));
+        CU_TRY(potential_launch(redo, P->cfg.mode, P->variant, grid, s));
     }
     CU_TRY(launch_energy_flag(lp, sm, s));
     CU_TRY(launch_halo_decide(lp, 0, sm, s));
@@ -1062,11 +1075,11 @@ static int enqueue_pass(halma_plan *P, int pass)
 {
     cudaStream_t s = P->stream;
     const int sm = P->ctx->sm_count;
-    const int grid = sm * P->ctx->bps[P->cfg.mode];
+    const int grid = sm * P->ctx->blocks(P->cfg.mode, P->variant);
     CU_TRY(cudaEventRecord(P->ev[3 * pass], s));
     if (P->np && P->cfg.n_ranks > 1)      // split mode: every correction entry is written by one rank only
         CU_TRY(cudaMemsetAsync(P->d_corr.p, 0, 3 * static_cast<size_t>(P->n_pad) * sizeof(double), s));
-    CU_TRY(potential_launch(P->pp, P->cfg.mode, grid, s));
+    CU_TRY(potential_launch(P->pp, P->cfg.mode, P->variant, grid, s));
     if (P->np) {
         // haloes whose predicate-free sums came out non-finite are recomputed with the predicate
         if (P->cfg.n_ranks > 1) {
@@ -1081,7 +1094,7 @@ static int enqueue_pass(halma_plan *P, int pass)
         }
         PotParams redo = P->pp;
         redo.redo_only = 1;
-        CU_TRY(potential_launch(redo, P->cfg.mode, grid, s));
+        CU_TRY(potential_launch(redo, P->cfg.mode, P->variant, grid, s));
     }
     CU_TRY(cudaEventRecord(P->ev[3 * pass + 1], s));
     if (P->cfg.n_ranks > 1) {

@@ -616,9 +616,11 @@ __global__ void __launch_bounds__(kPotentialBlock, 4) k_potential_exact(const Po
 // ---------------------------------------------------------------------------------------
 namespace {
 
-// Shapes of the FAST kernels: T targets per lane (group = 32 T targets per ticket) and the
-// minimum resident blocks per SM the register allocation is held to.  Variant 0 is the
-// default; HALMA_FAST_VARIANT=<index> selects another one (tuning sweeps).
+// Shapes of the FAST kernels: T targets per lane (a ticket = 32 T targets) and the minimum
+// resident blocks per SM the register allocation is held to.  Shape 0 is the throughput
+// shape; shape 1 (32 targets per ticket, 4x as many tickets) is picked when shape 0 could not
+// give every resident warp a ticket, i.e. for small haloes that are latency-bound.
+// HALMA_FAST_VARIANT=<index> forces one shape (tuning sweeps).
 struct FastVariant {
     int targets, min_blocks;
     void (*pred)(const PotParams);
@@ -627,27 +629,42 @@ struct FastVariant {
 
 #define HALMA_VARIANT(T, B) {T, B, k_potential_fast<T, B, false>, k_potential_fast<T, B, true>}
 const FastVariant kVariants[] = {
-    HALMA_VARIANT(4, 6), HALMA_VARIANT(4, 5), HALMA_VARIANT(4, 4), HALMA_VARIANT(2, 8),
+    HALMA_VARIANT(4, 6), HALMA_VARIANT(1, 8), HALMA_VARIANT(2, 8), HALMA_VARIANT(4, 4),
     HALMA_VARIANT(3, 6), HALMA_VARIANT(6, 3), HALMA_VARIANT(8, 3),
 };
 #undef HALMA_VARIANT
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-const FastVariant &fast_variant()
+int forced_variant()
 {
     static int idx = [] {
         const char *e = getenv("HALMA_FAST_VARIANT");
-        const int v = e ? atoi(e) : 0;
-        return (v >= 0 && v < kNumVariants) ? v : 0;
+        const int v = e ? atoi(e) : -1;
+        return (v >= 0 && v < kNumVariants) ? v : -1;
     }();
-    return kVariants[idx];
+    return idx;
 }
 
 }  // namespace
 
-int potential_group_size(int mode) { return mode == HALMA_MODE_EXACT ? 32 : 32 * fast_variant().targets; }
+int potential_num_variants() { return kNumVariants; }
 
-cudaError_t potential_configure(int mode, int *blocks_per_sm)
+int potential_pick_variant(int64_t groups_of_128, int64_t max_sources, int resident_warps)
+{
+    if (forced_variant() >= 0) return forced_variant();
+    // tickets the throughput shape would have after the j-split (at most kMaxSplit = 8 ways,
+    // pieces of >= 2048 sources): if that cannot occupy the resident warps, use small tickets
+    int64_t split = max_sources / 2048;
+    split = split < 1 ? 1 : (split > 8 ? 8 : split);
+    return groups_of_128 * split < resident_warps ? 1 : 0;
+}
+
+int potential_group_size(int mode, int variant)
+{
+    return mode == HALMA_MODE_EXACT ? 32 : 32 * kVariants[variant].targets;
+}
+
+cudaError_t potential_configure(int mode, int variant, int *blocks_per_sm)
 {
     cudaError_t e;
     if (mode == HALMA_MODE_EXACT) {
@@ -656,7 +673,7 @@ cudaError_t potential_configure(int mode, int *blocks_per_sm)
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_potential_exact, kPotentialBlock,
                                                              kSmemBytes);
     }
-    const FastVariant &v = fast_variant();
+    const FastVariant &v = kVariants[variant];
     e = cudaFuncSetAttribute(v.pred, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(v.np, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -669,14 +686,14 @@ cudaError_t potential_configure(int mode, int *blocks_per_sm)
     return e;
 }
 
-cudaError_t potential_launch(const PotParams &p, int mode, int grid_blocks, cudaStream_t stream)
+cudaError_t potential_launch(const PotParams &p, int mode, int variant, int grid_blocks, cudaStream_t stream)
 {
     if (mode == HALMA_MODE_EXACT)
         k_potential_exact<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else if (p.np_enabled && !p.redo_only)
-        fast_variant().np<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
+        kVariants[variant].np<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else
-        fast_variant().pred<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
+        kVariants[variant].pred<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 

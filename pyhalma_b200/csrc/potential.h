@@ -9,10 +9,16 @@ namespace halma {
 
 constexpr int kPotentialBlock = 128;     // 4 warps; each warp schedules itself
 
-// Targets per work item (warp): 32 (EXACT) or 32 * T (FAST, T = targets per lane of the variant).
-int potential_group_size(int mode);
+// FAST kernel shapes (potential.cu): index 0 = throughput shape (128 targets per ticket),
+// 1 = small-halo shape (32 targets per ticket).
+constexpr int kMaxVariants = 8;
+int potential_num_variants();
+// groups_of_128: sum over haloes of ceil(n_targets / 128); max_sources: largest source count.
+int potential_pick_variant(int64_t groups_of_128, int64_t max_sources, int resident_warps);
+// Targets per work item (warp): 32 (EXACT) or 32 * T (FAST, T = targets per lane of the shape).
+int potential_group_size(int mode, int variant);
 // Sets the dynamic shared-memory attribute and returns resident blocks per SM.
-cudaError_t potential_configure(int mode, int *blocks_per_sm);
-cudaError_t potential_launch(const PotParams &p, int mode, int grid_blocks, cudaStream_t stream);
+cudaError_t potential_configure(int mode, int variant, int *blocks_per_sm);
+cudaError_t potential_launch(const PotParams &p, int mode, int variant, int grid_blocks, cudaStream_t stream);
 
 }  // namespace halma
