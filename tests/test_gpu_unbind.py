@@ -513,3 +513,21 @@ def test_catalogue_fixed_bulk_velocity_per_halo():
         o = O.unbind_halo(*[c[a:b] for c in cols], kappa=2.0, vb_fixed=vb[h])
         assert np.array_equal(res.halo_mask(h), o.mask) and res.halos[h].n_iter == o.n_iter
         assert res.halos[h].vb == tuple(vb[h])
+
+
+def test_predicate_free_path_forced_on_small_and_odd_inputs():
+    """The predicate-free kernel + correction tickets normally engage above 4e9 pairs per pass.
+    Re-run the ragged / degenerate / duplicate / NaN / external-group / golden cases with the
+    threshold at zero so that every one of them goes through that path."""
+    import subprocess
+    import sys
+    if os.environ.get("HALMA_NP_MIN_PAIRS") == "0":
+        pytest.skip("already running with the threshold forced to zero")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HALMA_NP_MIN_PAIRS="0")
+    sel = ("ragged or degenerate or duplicates or zero_mass or external_groups or golden_fast or fused_large "
+           "or fast_mode_against or lattice or graph_loop or idempotence or rps_mass_sums")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_unbind.py"), "-q", "-x",
+                          "-m", "gpu", "-k", sel], capture_output=True, text=True, timeout=1200, env=env, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout
