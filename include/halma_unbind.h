@@ -216,6 +216,30 @@ int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n,
                       halma_halo_result *result, halma_run_stats *stats);
 
 /* ------------------------------------------------------------------------------------ *
+ * The other two routines of the f2py module `particle`, so that the
+ * module can be swapped without any Fortran toolchain.  HOST pointers, float32 like the
+ * f2py signatures; sums are accumulated in float64 on the device (the reference's float32
+ * OpenMP reductions are order-dependent, so parity is to ~1e-5, not bitwise).
+ *
+ * halma_halo_shape_f32: particle_subroutines.f90:160-214 (halo_shape, with DIAGONALISE
+ *   :12-126 and SORT_EIGEN :129-157): semi-axes a >= b >= c = square roots of the
+ *   eigenvalues of sum(m r_i r_j) / sum(m) of the (already centred) positions.
+ * halma_sigma_projections_f32: particle_subroutines.f90:217-461: line-of-sight velocity
+ *   dispersion inside R05 for the three projections, V/sigma and lambda_R averaged over
+ *   the projections, from n_cell x n_cell maps binned on `grid` (nearest grid point, first
+ *   minimum on ties).  part_list is 0-BASED here (the f2py shim subtracts the 1 the
+ *   reference's wrapper adds, halo_properties.py:787); n_all = length of the st_* arrays.
+ *   out5 = SIG_1D_x_05, SIG_1D_y_05, SIG_1D_z_05, V_sigma, lambda.
+ * ------------------------------------------------------------------------------------ */
+int halma_halo_shape_f32(int device, const float *x, const float *y, const float *z, const float *mass,
+                         int64_t npart, float *eigenvalues3);
+int halma_sigma_projections_f32(int device, int64_t npart, const float *grid, int32_t n_cell,
+                                const int32_t *part_list, int64_t n_all, const float *st_x, const float *st_y,
+                                const float *st_z, const float *st_vx, const float *st_vy, const float *st_vz,
+                                const float *st_mass, float cx, float cy, float cz, float R05x, float R05y,
+                                float R05z, float ll, float *out5);
+
+/* ------------------------------------------------------------------------------------ *
  * Pipe-rate microbenchmark used for the roofline denominator: measures
  * MUFU.RSQ, FFMA and packed FFMA2 issue rates per SM per clock, and the SM clock during
  * the measurement.  out: double[8] = {rsq_per_clk_sm, ffma_per_clk_sm, ffma2_per_clk_sm,

@@ -212,3 +212,233 @@ double oracle_wtime(void)
     return 0.0;
 #endif
 }
+
+/* ===========================================================================
+ * §8f-4: the other two routines of the f2py module `particle`.
+ * =========================================================================== */
+
+/* particle_subroutines.f90:12-126  DIAGONALISE: eigenvalues of a symmetric 3x3 matrix
+ * by cyclic Jacobi rotations, at most 100 sweeps, in double precision.  The input
+ * and the output are REAL*4 (:19); only the upper triangle is used. */
+void oracle_diagonalise(const float input[3][3], float eigen_out[3])
+{
+    double a[3][3], d[3], b[3], zacc[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) a[i][j] = (double)input[i][j];                 /* :29-33 */
+    for (int i = 0; i < 3; ++i) {
+        b[i] = a[i][i];
+        d[i] = b[i];
+        zacc[i] = 0.0;
+    }                                                                               /* :35-39 */
+    double sum_elements = 0.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) sum_elements += fabs(a[i][j]);                  /* :42-47 */
+    for (int sweep = 1; sweep <= 100; ++sweep) {                                    /* :50 */
+        double off = 0.0;
+        for (int i = 0; i < 2; ++i)
+            for (int j = i + 1; j < 3; ++j) off += fabs(a[i][j]);
+        if (off < (double)1.e-4f * sum_elements) break;        /* :57, `1.e-4` is a REAL*4 literal */
+        const double limit = sweep < 4 ? 0.2 * off * off : 0.0;                     /* :59-63 */
+        for (int i = 0; i < 2; ++i) {
+            for (int j = i + 1; j < 3; ++j) {
+                double g = 100.0 * fabs(a[i][j]);                                   /* :66 */
+                if (sweep > 4 && fabs(d[i]) + g == fabs(d[i]) && fabs(d[j]) + g == fabs(d[j])) {
+                    a[i][j] = 0.0;                                                  /* :68-72 */
+                } else if (fabs(a[i][j]) > limit) {
+                    double h = d[j] - d[i], t;
+                    if (fabs(h) + g == fabs(h)) {
+                        t = a[i][j] / h;                                            /* :75-76 */
+                    } else {
+                        const double theta = 0.5 * h / a[i][j];
+                        t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+                        if (theta < 0.0) t = -t;                                    /* :78-80 */
+                    }
+                    const double c = 1.0 / sqrt(1.0 + t * t), s = t * c, tau = s / (1.0 + c);
+                    h = t * a[i][j];
+                    zacc[i] -= h;
+                    zacc[j] += h;
+                    d[i] -= h;
+                    d[j] += h;
+                    a[i][j] = 0.0;                                                  /* :82-90 */
+                    for (int k = 0; k < i; ++k) {                                   /* :91-96 */
+                        const double p = a[k][i], q = a[k][j];
+                        a[k][i] = p - s * (q + p * tau);
+                        a[k][j] = q + s * (p - q * tau);
+                    }
+                    for (int k = i + 1; k < j; ++k) {                               /* :97-102 */
+                        const double p = a[i][k], q = a[k][j];
+                        a[i][k] = p - s * (q + p * tau);
+                        a[k][j] = q + s * (p - q * tau);
+                    }
+                    for (int k = j + 1; k < 3; ++k) {                               /* :103-108 */
+                        const double p = a[i][k], q = a[j][k];
+                        a[i][k] = p - s * (q + p * tau);
+                        a[j][k] = q + s * (p - q * tau);
+                    }
+                }
+            }
+        }
+        for (int i = 0; i < 3; ++i) {                                               /* :113-117 */
+            b[i] += zacc[i];
+            d[i] = b[i];
+            zacc[i] = 0.0;
+        }
+    }
+    for (int i = 0; i < 3; ++i) eigen_out[i] = (float)d[i];                         /* :121-123 */
+}
+
+/* particle_subroutines.f90:129-157  SORT_EIGEN: selection sort that moves the LARGEST
+ * value to the front (the header comment says increasing, the `.GE.` test says otherwise). */
+void oracle_sort_eigen(float *e, int n)
+{
+    for (int i = 0; i < n - 1; ++i) {
+        int k = i;
+        float v = e[i];
+        for (int j = i + 1; j < n; ++j)
+            if (e[j] >= v) {
+                k = j;
+                v = e[j];
+            }
+        if (k != i) {
+            e[k] = e[i];
+            e[i] = v;
+        }
+    }
+}
+
+/* particle_subroutines.f90:160-214  halo_shape: mass-weighted second-moment tensor of
+ * the (already centred) positions, normalised by the total mass, Jacobi eigenvalues,
+ * sorted largest first, square roots = semi-axes a >= b >= c.
+ * float32 accumulation in particle order (what one OpenMP thread does; with more threads
+ * the reference's REDUCTION changes the order and, as written, shares `rvec` between
+ * threads -- SURVEY.md §5 -- so only the one-thread semantics are well defined).
+ * wide = 1 accumulates in double: the accuracy anchor for the GPU path. */
+void oracle_halo_shape(int64_t npart, const float *x, const float *y, const float *z, const float *mass, int wide,
+                       float eigenvalues[3])
+{
+    float t32[3][3] = {{0}}, m32 = 0.f;
+    double t64[3][3] = {{0}}, m64 = 0.0;
+    for (int64_t ip = 0; ip < npart; ++ip) {
+        const float r[3] = {x[ip], y[ip], z[ip]};
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) {
+                if (wide)
+                    t64[i][j] += (double)mass[ip] * (double)r[i] * (double)r[j];
+                else
+                    t32[i][j] = t32[i][j] + mass[ip] * r[i] * r[j];                 /* :194 */
+            }
+        if (wide)
+            m64 += (double)mass[ip];
+        else
+            m32 = m32 + mass[ip];                                                   /* :197 */
+    }
+    float tn[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) tn[i][j] = wide ? (float)(t64[i][j] / m64) : t32[i][j] / m32;   /* :203 */
+    oracle_diagonalise(tn, eigenvalues);                                            /* :206 */
+    oracle_sort_eigen(eigenvalues, 3);                                              /* :207 */
+    for (int i = 0; i < 3; ++i) eigenvalues[i] = sqrtf(eigenvalues[i]);             /* :209-211 */
+}
+
+/* particle_subroutines.f90:217-461  sigma_projections.  part_list is 0-based here (the
+ * Python wrapper adds 1 for Fortran, halo_properties.py:787).  Maps are n_cell x n_cell,
+ * indexed [first + n_cell * second] like the Fortran (first, second) subscripts.
+ * wide = 1 keeps the maps and sums in double (accuracy anchor).
+ * out5 = SIG_1D_x_05, SIG_1D_y_05, SIG_1D_z_05, V_sigma, lambda. */
+static int nearest_cell(const float *grid, int n_cell, float d)
+{
+    int best = 0;                       /* minloc(abs(grid - d), dim = 1): first minimum */
+    float bv = fabsf(grid[0] - d);
+    for (int k = 1; k < n_cell; ++k) {
+        const float v = fabsf(grid[k] - d);
+        if (v < bv) {
+            bv = v;
+            best = k;
+        }
+    }
+    return best;
+}
+
+#include <stdlib.h>
+#define SIGMA_BODY(REAL, SQRT, FABS)                                                                          \
+    const size_t nn = (size_t)n_cell * n_cell;                                                                \
+    REAL *vcm[3], *sd[3], *sig[3];                                                                            \
+    int *cnt[3];                                                                                              \
+    for (int a = 0; a < 3; ++a) {                                                                             \
+        vcm[a] = (REAL *)calloc(nn, sizeof(REAL));                                                            \
+        sd[a] = (REAL *)calloc(nn, sizeof(REAL));                                                             \
+        sig[a] = (REAL *)calloc(nn, sizeof(REAL));                                                            \
+        cnt[a] = (int *)calloc(nn, sizeof(int));                                                              \
+    }                                                                                                         \
+    int *cell = (int *)malloc(sizeof(int) * 3 * (size_t)(npart > 0 ? npart : 1));                             \
+    for (int64_t ip = 0; ip < npart; ++ip) {                                       /* :264-281 */            \
+        const int64_t q = part_list[ip];                                                                      \
+        const int ix = nearest_cell(grid, n_cell, st_x[q] - cx), iy = nearest_cell(grid, n_cell, st_y[q] - cy), \
+                  iz = nearest_cell(grid, n_cell, st_z[q] - cz);                                              \
+        cell[3 * ip] = ix; cell[3 * ip + 1] = iy; cell[3 * ip + 2] = iz;                                      \
+        const size_t kx = iy + (size_t)n_cell * iz, ky = ix + (size_t)n_cell * iz, kz = ix + (size_t)n_cell * iy; \
+        vcm[0][kx] += (REAL)st_vx[q] * (REAL)st_mass[q]; vcm[1][ky] += (REAL)st_vy[q] * (REAL)st_mass[q];         \
+        vcm[2][kz] += (REAL)st_vz[q] * (REAL)st_mass[q];                                                          \
+        sd[0][kx] += st_mass[q]; sd[1][ky] += st_mass[q]; sd[2][kz] += st_mass[q];                            \
+        cnt[0][kx]++; cnt[1][ky]++; cnt[2][kz]++;                                                             \
+    }                                                                                                         \
+    for (int a = 0; a < 3; ++a)                                                    /* :286-288 */            \
+        for (size_t k = 0; k < nn; ++k)                                                                       \
+            if (sd[a][k] != 0) vcm[a][k] = vcm[a][k] / sd[a][k];                                              \
+    for (int64_t ip = 0; ip < npart; ++ip) {                                       /* :296-306 */            \
+        const int64_t q = part_list[ip];                                                                      \
+        const int ix = cell[3 * ip], iy = cell[3 * ip + 1], iz = cell[3 * ip + 2];                            \
+        const size_t kx = iy + (size_t)n_cell * iz, ky = ix + (size_t)n_cell * iz, kz = ix + (size_t)n_cell * iy; \
+        const REAL ax_ = (REAL)st_vx[q] - vcm[0][kx], ay_ = (REAL)st_vy[q] - vcm[1][ky],                      \
+                   az_ = (REAL)st_vz[q] - vcm[2][kz];                                                         \
+        sig[0][kx] += ax_ * ax_; sig[1][ky] += ay_ * ay_; sig[2][kz] += az_ * az_;                            \
+    }                                                                                                         \
+    for (int a = 0; a < 3; ++a)                                                    /* :310-312 */            \
+        for (size_t k = 0; k < nn; ++k)                                                                       \
+            if (cnt[a][k] != 0) sig[a][k] = SQRT(sig[a][k] / cnt[a][k]);                                      \
+    REAL s05[3] = {0, 0, 0};                                                                                  \
+    int c05[3] = {0, 0, 0};                                                                                   \
+    const float r05[3] = {R05x, R05y, R05z};                                                                  \
+    for (int64_t ip = 0; ip < npart; ++ip) {                                       /* :326-352 */            \
+        const int64_t q = part_list[ip];                                                                      \
+        const float dx = st_x[q] - cx, dy = st_y[q] - cy, dz = st_z[q] - cz;                                  \
+        const int ix = cell[3 * ip], iy = cell[3 * ip + 1], iz = cell[3 * ip + 2];                            \
+        const float dist[3] = {sqrtf(dy * dy + dz * dz), sqrtf(dx * dx + dz * dz), sqrtf(dx * dx + dy * dy)}; \
+        const size_t k3[3] = {iy + (size_t)n_cell * iz, ix + (size_t)n_cell * iz, ix + (size_t)n_cell * iy};  \
+        for (int a = 0; a < 3; ++a)                                                                           \
+            if (dist[a] < r05[a]) { s05[a] += sig[a][k3[a]]; c05[a]++; }                                      \
+    }                                                                                                         \
+    for (int a = 0; a < 3; ++a) out5[a] = (float)(c05[a] > 0 ? s05[a] / c05[a] : s05[a]);   /* :356-366 */   \
+    REAL vs[3] = {0, 0, 0}, lam[3] = {0, 0, 0};                                                               \
+    for (int a = 0; a < 3; ++a) {            /* a = 2: XY plane (:380-401), 1: XZ (:404-424), 0: YZ (:427-448) */ \
+        REAL sumV = 0, sumS = 0, up = 0, down = 0;                                                            \
+        for (int j = 0; j < n_cell; ++j)                                                                      \
+            for (int i = 0; i < n_cell; ++i) {                                                                \
+                const float rbin = sqrtf(grid[i] * grid[i] + grid[j] * grid[j]);                              \
+                if (rbin < r05[a] + 2 * ll) {                                                                 \
+                    const size_t k = i + (size_t)n_cell * j;                                                  \
+                    sumV += vcm[a][k] * vcm[a][k] * sd[a][k];                                                 \
+                    sumS += sig[a][k] * sig[a][k] * sd[a][k];                                                 \
+                    up += sd[a][k] * rbin * FABS(vcm[a][k]);                                                  \
+                    down += sd[a][k] * rbin * SQRT(vcm[a][k] * vcm[a][k] + sig[a][k] * sig[a][k]);            \
+                }                                                                                             \
+            }                                                                                                 \
+        if (sumS > 0) vs[a] = SQRT(sumV / sumS);                                                              \
+        if (down > 0) lam[a] = up / down;                                                                     \
+    }                                                                                                         \
+    out5[3] = (float)((vs[0] + vs[1] + vs[2]) / 3);                                /* :453-454 */            \
+    out5[4] = (float)((lam[0] + lam[1] + lam[2]) / 3);                                                        \
+    for (int a = 0; a < 3; ++a) { free(vcm[a]); free(sd[a]); free(sig[a]); free(cnt[a]); }                    \
+    free(cell);
+
+void oracle_sigma_projections(int64_t npart, const float *grid, int n_cell, const int32_t *part_list,
+                              const float *st_x, const float *st_y, const float *st_z, const float *st_vx,
+                              const float *st_vy, const float *st_vz, const float *st_mass, float cx, float cy,
+                              float cz, float R05x, float R05y, float R05z, float ll, int wide, float out5[5])
+{
+    if (wide) {
+        SIGMA_BODY(double, sqrt, fabs)
+    } else {
+        SIGMA_BODY(float, sqrtf, fabsf)
+    }
+}

@@ -59,6 +59,14 @@ def lib() -> ctypes.CDLL:
                                                      _F32P, _F32P, _F32P, _F32P]
         L.oracle_count_excluded.restype = i64
         L.oracle_count_excluded.argtypes = [i64, _F32P, _F32P, _F32P, i64, _F32P, _F32P, _F32P]
+        I32P = ctypes.POINTER(ctypes.c_int32)
+        L.oracle_halo_shape.restype = None
+        L.oracle_halo_shape.argtypes = [i64, _F32P, _F32P, _F32P, _F32P, ctypes.c_int, _F32P]
+        L.oracle_diagonalise.restype = None
+        L.oracle_diagonalise.argtypes = [_F32P, _F32P]
+        L.oracle_sigma_projections.restype = None
+        L.oracle_sigma_projections.argtypes = ([i64, _F32P, ctypes.c_int, I32P] + [_F32P] * 7 + [ctypes.c_float] * 7
+                                               + [ctypes.c_int, _F32P])
         L.oracle_max_threads.restype = ctypes.c_int
         L.oracle_wtime.restype = ctypes.c_double
         _lib = L
@@ -131,11 +139,70 @@ def serial_brute_force_binding_energy(ntotal, total_mass, total_x, total_y, tota
     return out
 
 
+# --------------------------------------------------------------------------------------
+# §8f-4: particle.halo_shape (particle_subroutines.f90:160-214) and
+# particle.sigma_projections (:217-461), f2py signatures.
+# --------------------------------------------------------------------------------------
+def diagonalise(matrix3x3):
+    m = np.ascontiguousarray(matrix3x3, dtype=np.float32).reshape(3, 3)
+    out = np.zeros(3, np.float32)
+    lib().oracle_diagonalise(_p32(m.reshape(-1)), _p32(out))
+    return out
+
+
+def halo_shape(ncore, npart, x, y, z, mass, *, wide: bool = False):
+    x, y, z, mass = map(_f32c, (x, y, z, mass))
+    _check_f2py_shapes(npart, (x, y, z, mass), npart, ())
+    out = np.zeros(3, np.float32)
+    lib().oracle_halo_shape(int(npart), _p32(x), _p32(y), _p32(z), _p32(mass), int(wide), _p32(out))
+    return out
+
+
+def sigma_projections(ncore, npart, grid, n_cell, part_list, st_x, st_y, st_z, st_vx, st_vy, st_vz, st_mass,
+                      cx, cy, cz, R05x, R05y, R05z, ll, *, wide: bool = False):
+    """part_list is 1-based, exactly what the reference hands to Fortran (halo_properties.py:787)."""
+    grid = _f32c(grid)
+    pl = np.ascontiguousarray(part_list, dtype=np.int32) - 1
+    arrs = [_f32c(a) for a in (st_x, st_y, st_z, st_vx, st_vy, st_vz, st_mass)]
+    if len(pl) != int(npart) or len(grid) != int(n_cell):
+        raise ValueError("0-th dimension must be fixed")
+    if len(pl) and (pl.min() < 0 or pl.max() >= len(arrs[0])):
+        raise IndexError("part_list out of range")
+    out = np.zeros(5, np.float32)
+    lib().oracle_sigma_projections(int(npart), _p32(grid), int(n_cell), pl.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                   *[_p32(a) for a in arrs], float(cx), float(cy), float(cz), float(R05x),
+                                   float(R05y), float(R05z), float(ll), int(wide), _p32(out))
+    return tuple(out)
+
+
+def halo_shape_fortran(part_list, st_x, st_y, st_z, st_mass, cx, cy, cz, RAD05, *, wide=False):
+    """python_scripts/halo_properties.py:852-866."""
+    x = np.float32(st_x[part_list] - cx)
+    y = np.float32(st_y[part_list] - cy)
+    z = np.float32(st_z[part_list] - cz)
+    mass = np.float32(st_mass[part_list])
+    e = halo_shape(np.int32(max_threads()), np.int32(len(part_list)), x, y, z, mass, wide=wide)
+    return e[0], e[1], e[2]
+
+
+def sigma_projections_fortran(grid, n_cell, part_list, st_x, st_y, st_z, st_vx, st_vy, st_vz, vx, vy, vz, st_mass,
+                              cx, cy, cz, R05x, R05y, R05z, ll, *, wide=False):
+    """python_scripts/halo_properties.py:781-812: float32 casts, velocities relative to the
+    bulk velocity, part_list + 1 for Fortran."""
+    return sigma_projections(np.int32(max_threads()), np.int32(len(part_list)), np.float32(grid), np.int32(n_cell),
+                             np.int32(1 + part_list), np.float32(st_x), np.float32(st_y), np.float32(st_z),
+                             np.float32(st_vx - vx), np.float32(st_vy - vy), np.float32(st_vz - vz),
+                             np.float32(st_mass), np.float32(cx), np.float32(cy), np.float32(cz), np.float32(R05x),
+                             np.float32(R05y), np.float32(R05z), np.float32(ll), wide=wide)
+
+
 class _ParticleNamespace:
     """Stands in for the f2py module object: `particle.particle.<routine>`
     (python_scripts/halo_gas.py:6,182)."""
     brute_force_binding_energy = staticmethod(brute_force_binding_energy)
     serial_brute_force_binding_energy = staticmethod(serial_brute_force_binding_energy)
+    halo_shape = staticmethod(halo_shape)
+    sigma_projections = staticmethod(sigma_projections)
 
 
 class particle_module:  # noqa: N801  (mirrors the f2py module name)

@@ -23,6 +23,7 @@ EXPORTS = (
     "halma_potential_f32_dev", "halma_plan_create", "halma_plan_destroy", "halma_plan_upload_members",
     "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join", "halma_comm_create", "halma_comm_destroy", "halma_plan_use_comm",
     "halma_plan_run", "halma_plan_download", "halma_unbind_halo", "halma_microbench",
+    "halma_halo_shape_f32", "halma_sigma_projections_f32",
 )
 
 
@@ -96,6 +97,8 @@ def lib() -> C.CDLL:
     L.halma_plan_run.argtypes = [vp, C.POINTER(RunStats)]
     L.halma_plan_download.argtypes = [vp, vp, vp, vp, vp, C.POINTER(HaloResult)]
     L.halma_microbench.argtypes = [i32, f64p]
+    L.halma_halo_shape_f32.argtypes = [i32, vp, vp, vp, vp, i64, vp]
+    L.halma_sigma_projections_f32.argtypes = ([i32, i64, vp, C.c_int32, vp, i64] + [vp] * 7 + [C.c_float] * 7 + [vp])
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("halma_last_error", "halma_potential_workspace_bytes", "halma_plan_destroy",

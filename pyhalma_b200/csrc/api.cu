@@ -95,6 +95,17 @@ static int get_ctx(int device, DeviceCtx **out)
     return HALMA_OK;
 }
 
+// Used by shape.cu: device context (lazy init), its stream and SM count.
+int halma_internal_ctx(int device, int *sm_count, cudaStream_t *stream)
+{
+    DeviceCtx *c;
+    if (int rc = get_ctx(device, &c)) return rc;
+    if (sm_count) *sm_count = c->sm_count;
+    if (stream) *stream = c->stream;
+    return HALMA_OK;
+}
+int halma_internal_fail(int code, const char *msg) { return fail(code, msg); }
+
 extern "C" int halma_device_count(int *count)
 {
     if (!count) return fail(HALMA_ERR_INVALID, "count is null");

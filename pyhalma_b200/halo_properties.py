@@ -4,12 +4,15 @@
   escape_velocity_unbinding_fortran              halo_properties.py:282-361
   escape_velocity_unbinding                      the same from :333 on, for inputs that
                                                  are already gathered, optionally iterated
+  halo_shape_fortran                             halo_properties.py:852-866
+  sigma_projections_fortran                      halo_properties.py:781-812
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import halo_gas
+from .particle import particle
 from .unbind import unbind_halo
 
 
@@ -66,3 +69,24 @@ def escape_velocity_unbinding_fortran(rete, L, ncoarse, grid_data, gas_data, mas
     gas = (gas_x[inside], gas_y[inside], gas_z[inside], gas_mass[inside] * rete ** 3)
     res = escape_velocity_unbinding(gas, stars, dm, (vx, vy, vz), factor_v, mode=mode, device=device)
     return res.mask
+
+
+def halo_shape_fortran(part_list, st_x, st_y, st_z, st_mass, cx, cy, cz, RAD05, *, device=0):
+    """Semi-axes (a, b, c) of the particle list, halo_properties.py:852-866."""
+    x = np.float32(st_x[part_list] - cx)
+    y = np.float32(st_y[part_list] - cy)
+    z = np.float32(st_z[part_list] - cz)
+    mass = np.float32(st_mass[part_list])
+    eigenvalues = particle.halo_shape(np.int32(1), np.int32(len(part_list)), x, y, z, mass, device=device)
+    return eigenvalues[0], eigenvalues[1], eigenvalues[2]
+
+
+def sigma_projections_fortran(grid, n_cell, part_list, st_x, st_y, st_z, st_vx, st_vy, st_vz, vx, vy, vz, st_mass,
+                              cx, cy, cz, R05x, R05y, R05z, ll, *, device=0):
+    """halo_properties.py:781-812: float32 casts, velocities relative to (vx, vy, vz),
+    part_list + 1 for the Fortran-style index base."""
+    return particle.sigma_projections(
+        np.int32(1), np.int32(len(part_list)), np.float32(grid), np.int32(n_cell), np.int32(1 + part_list),
+        np.float32(st_x), np.float32(st_y), np.float32(st_z), np.float32(st_vx - vx), np.float32(st_vy - vy),
+        np.float32(st_vz - vz), np.float32(st_mass), np.float32(cx), np.float32(cy), np.float32(cz),
+        np.float32(R05x), np.float32(R05y), np.float32(R05z), np.float32(ll), device=device)

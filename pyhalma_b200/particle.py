@@ -7,8 +7,9 @@ the `!f2py depend(...)` directives at :485-488 keep ntotal / ntest as required a
 and the same return value (a fresh float32 array of length ntest), computed on the B200.
 
 `ncores` is accepted and ignored.  Shape mismatches raise ValueError like the f2py shim.
-`halo_shape` / `sigma_projections` (particle_subroutines.f90:12-461) are outside the
-replaced path; when the original f2py module is importable they are forwarded to it.
+`halo_shape` and `sigma_projections` (particle_subroutines.f90:160-214, :217-461), the other
+two routines of the module, run on the GPU as well, so the swap needs no
+Fortran toolchain.
 """
 from __future__ import annotations
 
@@ -64,20 +65,36 @@ class particle:  # noqa: N801  (the Fortran MODULE name inside the f2py extensio
                           mode, device)
 
     @staticmethod
-    def _forward(name):
-        try:
-            import importlib
-            orig = importlib.import_module("fortran_modules._particle_f2py")
-        except Exception as exc:  # pragma: no cover - needs the reference build
-            raise NotImplementedError(
-                "particle.%s is outside the replaced hot path; keep the original f2py build as "
-                "fortran_modules/_particle_f2py to forward it (INTEGRATION.md)" % name) from exc
-        return getattr(orig.particle, name)
+    def halo_shape(ncore, npart, x, y, z, mass, *, device=0):
+        """particle_subroutines.f90:160-214: semi-axes a >= b >= c (float32[3]) of the
+        mass-weighted second-moment tensor of the centred positions."""
+        del ncore
+        npart = int(npart)
+        xs = [_as_f32(a, npart, n) for a, n in ((x, "x"), (y, "y"), (z, "z"), (mass, "mass"))]
+        out = np.zeros(3, dtype=np.float32)
+        _lib.check(_lib.lib().halma_halo_shape_f32(device, *[a.ctypes.data for a in xs], npart, out.ctypes.data))
+        return out
 
     @staticmethod
-    def halo_shape(*args, **kw):  # pragma: no cover
-        return particle._forward("halo_shape")(*args, **kw)
-
-    @staticmethod
-    def sigma_projections(*args, **kw):  # pragma: no cover
-        return particle._forward("sigma_projections")(*args, **kw)
+    def sigma_projections(ncore, npart, grid, n_cell, part_list, st_x, st_y, st_z, st_vx, st_vy, st_vz, st_mass,
+                          cx, cy, cz, R05x, R05y, R05z, ll, *, device=0):
+        """particle_subroutines.f90:217-461.  part_list is 1-based, as the reference's wrapper
+        passes it (halo_properties.py:787).  Returns (SIG_1D_x_05, SIG_1D_y_05, SIG_1D_z_05,
+        V_sigma, lambda) as Python floats, like f2py."""
+        del ncore
+        npart, n_cell = int(npart), int(n_cell)
+        g = _as_f32(grid, n_cell, "grid")
+        pl = np.ascontiguousarray(part_list, dtype=np.int32)
+        if pl.ndim != 1 or pl.shape[0] != npart:
+            raise ValueError("part_list: 0-th dimension must be fixed to %d but got %d" % (npart, pl.shape[0]))
+        pl = pl - np.int32(1)
+        n_all = len(st_x)
+        arrs = [_as_f32(a, n_all, n) for a, n in ((st_x, "st_x"), (st_y, "st_y"), (st_z, "st_z"), (st_vx, "st_vx"),
+                                                  (st_vy, "st_vy"), (st_vz, "st_vz"), (st_mass, "st_mass"))]
+        if npart and (pl.min() < 0 or pl.max() >= n_all):
+            raise IndexError("part_list out of range")
+        out = np.zeros(5, dtype=np.float32)
+        _lib.check(_lib.lib().halma_sigma_projections_f32(
+            device, npart, g.ctypes.data, n_cell, pl.ctypes.data, n_all, *[a.ctypes.data for a in arrs],
+            float(cx), float(cy), float(cz), float(R05x), float(R05y), float(R05z), float(ll), out.ctypes.data))
+        return tuple(float(v) for v in out)

@@ -51,6 +51,14 @@ class _RecordingParticle:
         CALLS.append((int(ntotal), int(ntest), out.copy()))
         return out
 
+    @staticmethod
+    def halo_shape(ncore, npart, x, y, z, mass):
+        return O.halo_shape(ncore, npart, x, y, z, mass)
+
+    @staticmethod
+    def sigma_projections(*args):
+        return O.sigma_projections(*args)
+
 
 def install_stubs():
     mf = types.ModuleType("masclet_framework")
@@ -171,5 +179,37 @@ def main():
     print("stellar_onepass bound", int(np.sum(bound)), "of", len(bound))
 
 
+def shape_and_sigma():
+    """halo_properties.halo_shape_fortran (:852-866) and sigma_projections_fortran (:781-812),
+    the reference's own wrappers, on a triaxial rotating toy galaxy."""
+    from python_scripts import halo_properties
+    rng = np.random.default_rng(31)
+    n_glob, n = 6000, 4500
+    part_list = np.sort(rng.choice(n_glob, n, replace=False))
+    st_x = 3.0 + rng.normal(0, 3e-3, n_glob)
+    st_y = -7.0 + rng.normal(0, 2e-3, n_glob)
+    st_z = 11.0 + rng.normal(0, 1e-3, n_glob)
+    st_mass = rng.uniform(0.5e6, 2e6, n_glob)
+    st_vx = 150.0 + rng.normal(0, 60, n_glob) - 2.0e4 * (st_y + 7.0)
+    st_vy = -80.0 + rng.normal(0, 60, n_glob) + 2.0e4 * (st_x - 3.0)
+    st_vz = 40.0 + rng.normal(0, 40, n_glob)
+    cx, cy, cz, M = halo_properties.center_of_mass(part_list, st_x, st_y, st_z, st_mass)
+    vx, vy, vz = halo_properties.CM_velocity(M, part_list, st_vx, st_vy, st_vz, st_mass)
+    rad05 = 3e-3
+    abc = halo_properties.halo_shape_fortran(part_list, st_x, st_y, st_z, st_mass, cx, cy, cz, rad05)
+    ll = 0.5e-3
+    n_cell = 25
+    grid = (np.arange(n_cell) - n_cell // 2) * ll
+    sig = halo_properties.sigma_projections_fortran(grid, n_cell, part_list, st_x, st_y, st_z, st_vx, st_vy, st_vz,
+                                                    vx, vy, vz, st_mass, cx, cy, cz, rad05, 0.8 * rad05, 0.6 * rad05, ll)
+    np.savez_compressed(os.path.join(HERE, "shape_sigma.npz"), part_list=part_list, st_x=st_x, st_y=st_y, st_z=st_z,
+                        st_vx=st_vx, st_vy=st_vy, st_vz=st_vz, st_mass=st_mass, com=np.array([cx, cy, cz]),
+                        vb=np.array([vx, vy, vz]), rad05=np.float64(rad05), ll=np.float64(ll), grid=grid,
+                        n_cell=np.int64(n_cell), abc=np.array(abc, dtype=np.float32),
+                        sigma=np.array(sig, dtype=np.float32))
+    print("shape_sigma abc", abc, "sigma", sig)
+
+
 if __name__ == "__main__":
     main()
+    shape_and_sigma()

@@ -51,6 +51,16 @@ def test_argument_validation_without_gpu():
     assert L.halma_potential_f32(0, 0, None, None, None, None, -1, None, None, None, 0, None) == _lib.ERR_INVALID
     assert L.halma_potential_f32(0, 0, None, None, None, None, 0, None, None, None, 0, None) == _lib.HALMA_OK
     assert L.halma_potential_workspace_bytes(10, 10) >= 1024 + 8 * 12 * 8
+    assert L.halma_halo_shape_f32(0, None, None, None, None, 3, None) == _lib.ERR_INVALID
+    e3 = np.zeros(3, np.float32)
+    assert L.halma_halo_shape_f32(0, None, None, None, None, 3, e3.ctypes.data) == _lib.ERR_INVALID
+    g3 = np.zeros(3, np.float32)
+    o5 = np.zeros(5, np.float32)
+    bad = np.array([7], np.int32)
+    one = np.zeros(1, np.float32)
+    assert L.halma_sigma_projections_f32(0, 1, g3.ctypes.data, 3, bad.ctypes.data, 1, *[one.ctypes.data] * 7,
+                                         0., 0., 0., 1., 1., 1., .5, o5.ctypes.data) == _lib.ERR_INVALID
+    assert b"part_list" in L.halma_last_error()
     cfg = _lib.UnbindConfig()
     cfg.struct_size = 12          # wrong size -> ABI guard
     h = ctypes.c_void_p()

@@ -19,7 +19,11 @@ def test_dropin_attribute_path_and_signatures():
         "pg = [p.name for p in inspect.signature(g).parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]\n"
         "assert pf == ['ncores','ntotal','total_mass','total_x','total_y','total_z','ntest','test_x','test_y','test_z'], pf\n"
         "assert pg == pf[1:], pg\n"
-        "assert hasattr(particle.particle, 'halo_shape') and hasattr(particle.particle, 'sigma_projections')\n"
+        "ps = [p.name for p in inspect.signature(particle.particle.halo_shape).parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]\n"
+        "assert ps == ['ncore','npart','x','y','z','mass'], ps\n"          # particle_subroutines.f90:160
+        "pq = [p.name for p in inspect.signature(particle.particle.sigma_projections).parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]\n"
+        "assert pq == ['ncore','npart','grid','n_cell','part_list','st_x','st_y','st_z','st_vx','st_vy','st_vz','st_mass',"
+        "'cx','cy','cz','R05x','R05y','R05z','ll'], pq\n"                  # particle_subroutines.f90:217-219"
         "print('ok')\n" % (os.path.join(ROOT, "dropin"), ROOT))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
