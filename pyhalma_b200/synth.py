@@ -323,3 +323,102 @@ def config5(n_gas: int = 10_000_000, n_star: int = 2_000_000, n_dm: int = 500_00
     gas = lattice_gas(n_gas, 4 * CELL, rng, m_total=0.1 * n_star * 1e6, two_levels=True)
     dm = dm_cloud(n_dm, 200 * KPC, 8e7, rng)
     return HaloCase(stars, gas, dm, mass_dm_part=8e7, name="cfg5")
+
+
+# --------------------------------------------------------------------------------------
+# A synthetic MASCLET-like AMR snapshot: the input format of the gather step before the
+# hot path (python_scripts/halo_gas.py:56-141, 223-277)
+# --------------------------------------------------------------------------------------
+@dataclass
+class AmrSnapshot:
+    """The objects pyHALMA.py hands to halo_gas.st_gas_dm_particles_inside (:1027-1037), with
+    only the entries that function reads filled in:
+      grid_data[2] nl, [5] npatch per level (npatch[0] = 0), [6..8] patchnx/ny/nz, [12..14]
+      patchrx/ry/rz (centre of the patch's first PARENT cell), index 0 = the base grid;
+      gas_data[0] delta, [1..3] velocity in units of c, [4] temperature, [5] cr0amr (True =
+      not refined), [6] solapst (True = not overlapped): per-patch (nx, ny, nz) arrays,
+      float32 / bool, Fortran-ordered like masclet_framework's reader returns them;
+      masclet_dm_data[0..3] x, y, z, mass; masclet_st_data[0..2] position, [6] mass, [9] id."""
+    L: float
+    ncoarse: int
+    grid_data: list
+    gas_data: list
+    masclet_dm_data: list
+    masclet_st_data: list
+    rho_B: float
+    rete: float
+    centre: tuple
+
+    @property
+    def n_cells(self) -> int:
+        return int(sum(int(a.size) for a in self.gas_data[0][1:]))
+
+
+def amr_snapshot(n_levels: int = 5, patches_per_level: int = 3, n_dm: int = 20_000, n_st: int = 30_000,
+                 seed_extra: int = 0, L: float = 40.0, ncoarse: int = 128, centre=CENTRE,
+                 max_cells: int = 28, base_cells: int = 4) -> AmrSnapshot:
+    """Nested patches around `centre`: level l has `patches_per_level` patches of up to
+    max_cells^3 cells of size (L/ncoarse)/2^l, aligned to the parent grid, partly overlapping;
+    cr0amr marks cells covered by a finer patch, solapst cells already covered by an earlier
+    patch of the same level; a few flags are flipped at random."""
+    rng = rng_for(6, seed_extra)
+    c = np.asarray(centre, dtype=np.float64)
+    npatch = [0]
+    nx, ny, nz = [ncoarse], [ncoarse], [ncoarse]
+    rx, ry, rz = [-L / 2 + L / ncoarse / 2] * 1, [-L / 2 + L / ncoarse / 2], [-L / 2 + L / ncoarse / 2]
+    level_of = [0]
+    lo_edges = [np.full(3, -L / 2)]
+    for lev in range(1, n_levels + 1):
+        res = (L / ncoarse) / 2 ** lev
+        npatch.append(patches_per_level)
+        for _ in range(patches_per_level):
+            n = 2 * rng.integers(4, max_cells // 2 + 1, 3)              # even: whole parent cells
+            jitter = rng.integers(-3, 4, 3) * 2 * res
+            left = c - n * res / 2 + jitter
+            left = -L / 2 + np.round((left + L / 2) / (2 * res)) * (2 * res)     # parent-cell edges
+            nx.append(int(n[0])); ny.append(int(n[1])); nz.append(int(n[2]))
+            rx.append(left[0] + res); ry.append(left[1] + res); rz.append(left[2] + res)
+            level_of.append(lev)
+            lo_edges.append(left)
+    npt = len(nx)
+    nxa, nya, nza = (np.array(a, dtype=np.int64) for a in (nx, ny, nz))
+    hi_edges = [lo_edges[p] + np.array([nx[p], ny[p], nz[p]]) * (L / ncoarse) / 2 ** level_of[p] for p in range(npt)]
+    delta, vx, vy, vz, temp, cr0, sol = ([None] * npt for _ in range(7))
+    bc = base_cells                                     # the base grid is never read (l = 0 is skipped)
+    for p in range(npt):
+        shape = (bc, bc, bc) if p == 0 else (nx[p], ny[p], nz[p])
+        res = (L / ncoarse) / 2 ** level_of[p]
+        ax = [lo_edges[p][k] + (np.arange(shape[k]) + 0.5) * res for k in range(3)]
+        X, Y, Z = np.meshgrid(*ax, indexing="ij")
+        r = np.sqrt((X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2)
+        rc = 20 * KPC
+        d = 2e4 / (1 + (r / rc) ** 2) ** 1.5 * rng.lognormal(0, 0.3, shape) - 0.5
+        delta[p] = np.asfortranarray(d.astype(np.float32))
+        for arr, v0, sig in ((vx, BULK_V[0], 120.0), (vy, BULK_V[1], 120.0), (vz, BULK_V[2], 120.0)):
+            arr[p] = np.asfortranarray(((v0 + rng.normal(0, sig, shape)) / 3e5).astype(np.float32))
+        temp[p] = np.asfortranarray((10 ** rng.uniform(3, 7, shape)).astype(np.float32))
+        refined = np.zeros(shape, dtype=bool)
+        overl = np.zeros(shape, dtype=bool)
+        for q in range(1, npt):
+            if q == p or p == 0:
+                continue
+            inside = ((X > lo_edges[q][0]) & (X < hi_edges[q][0]) & (Y > lo_edges[q][1]) & (Y < hi_edges[q][1])
+                      & (Z > lo_edges[q][2]) & (Z < hi_edges[q][2]))
+            if level_of[q] == level_of[p] + 1:
+                refined |= inside
+            elif level_of[q] == level_of[p] and q < p:
+                overl |= inside
+        flip = rng.uniform(0, 1, shape) < 0.01
+        cr0[p] = np.asfortranarray(~refined ^ flip)
+        sol[p] = np.asfortranarray(~overl ^ (rng.uniform(0, 1, shape) < 0.01))
+    grid_data = [None] * 15
+    grid_data[2] = n_levels
+    grid_data[5] = np.array(npatch, dtype=np.int64)
+    grid_data[6], grid_data[7], grid_data[8] = nxa, nya, nza
+    grid_data[12], grid_data[13], grid_data[14] = (np.array(a, dtype=np.float64) for a in (rx, ry, rz))
+    gas_data = [delta, vx, vy, vz, temp, cr0, sol]
+    dm = dm_cloud(n_dm, 60 * KPC, 8e7 / 8, rng, centre=centre)
+    st = plummer_stars(n_st, 8 * KPC, 1e6, rng, centre=centre)
+    dm_data = [dm.x, dm.y, dm.z, dm.mass]
+    st_data = [st.x, st.y, st.z, st.vx, st.vy, st.vz, st.mass, None, None, np.arange(n_st, dtype=np.int64) + 7_000_000]
+    return AmrSnapshot(L, ncoarse, grid_data, gas_data, dm_data, st_data, rho_B=3.9e10, rete=0.8, centre=tuple(c))

@@ -67,6 +67,11 @@ def install_stubs():
         setattr(mf, sub, m)
         sys.modules["masclet_framework." + sub] = m
     mf.units.mass_to_sun = 1.0
+    # un-vendored masclet_framework.tools helpers the gather calls (halo_gas.py:91-92), restated
+    # from their published behaviour in oracle/gather.py (see its header)
+    from oracle import gather as OG
+    mf.tools.which_patches_inside_box = OG.which_patches_inside_box
+    mf.tools.create_vector_levels = OG.create_vector_levels
     sys.modules["masclet_framework"] = mf
     mpl = types.ModuleType("matplotlib")
     plt = types.ModuleType("matplotlib.pyplot")
@@ -210,6 +215,52 @@ def shape_and_sigma():
     print("shape_sigma abc", abc, "sigma", sig)
 
 
+GATHER_CASES = (  # (tag, radius in Mpc, centre offset in Mpc)
+    ("r10", 0.010, (0.0, 0.0, 0.0)),
+    ("r25off", 0.025, (0.004, -0.006, 0.002)),
+    ("r60", 0.060, (-0.01, 0.0, 0.02)),
+    ("tiny", 0.0004, (0.0, 0.0, 0.0)),
+)
+GATHER_SNAPSHOT = dict(n_levels=7, n_dm=20_000, n_st=30_000)
+GATHER_FULL_MAX = 600          # cases with more gas particles than this are stored as sha256 digests
+
+
+def gather_amr():
+    """halo_gas.st_gas_dm_particles_inside (:223-277), the reference's own function with the real
+    numba patch_to_particles and real scipy KD-trees, on synth.amr_snapshot(**GATHER_SNAPSHOT).
+    The inputs are regenerated from the seed by the tests; only outputs are stored: in canonical
+    order (oracle/gather.py::canonical_gather), as arrays for small cases and as sha256 digests
+    of the arrays' bytes for large ones."""
+    import importlib
+
+    from scipy.spatial import KDTree
+
+    from oracle import gather as OG
+    from python_scripts import halo_gas
+    importlib.reload(halo_gas)                      # undo the AMRgrid_to_particles stub of main()
+    snap = synth.amr_snapshot(**GATHER_SNAPSHOT)
+    dm_tree = KDTree(np.array(snap.masclet_dm_data[:3]).T)
+    st_tree = KDTree(np.array(snap.masclet_st_data[:3]).T)
+    d = {"n_cells": np.int64(snap.n_cells), "tags": np.array([c[0] for c in GATHER_CASES])}
+    for tag, R, off in GATHER_CASES:
+        cx, cy, cz = (snap.centre[k] + off[k] for k in range(3))
+        out = halo_gas.st_gas_dm_particles_inside(snap.rete, snap.L, snap.ncoarse, snap.grid_data, snap.gas_data,
+                                                  snap.masclet_dm_data, snap.masclet_st_data, st_tree, dm_tree,
+                                                  cx, cy, cz, R, snap.rho_B)
+        out = OG.canonical_gather(out)
+        full = len(out[0]) <= GATHER_FULL_MAX
+        for n, a in zip(OG.GATHER_NAMES, out):
+            assert a.dtype in (np.float64, np.int64), (n, a.dtype)
+            if full and n.startswith("gas"):
+                d["%s_%s" % (tag, n)] = a
+            d["%s_sha_%s" % (tag, n)] = OG.digest(a)
+        d[tag + "_args"] = np.array([cx, cy, cz, R])
+        d[tag + "_counts"] = np.array([len(out[0]), len(out[8]), len(out[12])])
+        print("gather", tag, "gas", len(out[0]), "dm", len(out[8]), "stars", len(out[12]))
+    np.savez_compressed(os.path.join(HERE, "gather_amr.npz"), **d)
+
+
 if __name__ == "__main__":
     main()
     shape_and_sigma()
+    gather_amr()
