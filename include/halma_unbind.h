@@ -240,6 +240,47 @@ int halma_sigma_projections_f32(int device, int64_t npart, const float *grid, in
                                 float R05z, float ll, float *out5);
 
 /* ------------------------------------------------------------------------------------ *
+ * The gather step before the path: python_scripts/halo_gas.py:223-277
+ * (st_gas_dm_particles_inside) with :9-52 (patch_to_particles), :56-141
+ * (AMRgrid_to_particles), :216-218 (parallel_inside) and the KD-tree ball queries :255,:269.
+ * A snapshot (AMR hierarchy + cell fields + DM + star particles) is uploaded ONCE and stays
+ * in HBM; every halo then costs one halma_snapshot_gather.
+ *
+ * halma_snapshot_create: the patches as masclet's grid_data gives them, index 0 = base
+ *   grid: level[p], extent nx/ny/nz[p] (cells of level[p]), rx/ry/rz[p] = centre of the
+ *   patch's first PARENT cell.  Patches of level 0 are never read (halo_gas.py:107).
+ * halma_snapshot_upload_patch: cell fields of one patch, C-ordered (ix slowest, iz fastest =
+ *   the reference's loop nest): delta = rho/rho_B - 1, velocity in units of c, temperature
+ *   (float32); cr0amr != 0 = not refined, solapst != 0 = not overlapped (uint8).  Patches that
+ *   were never uploaded contribute nothing.
+ * halma_snapshot_upload_particles: kind 0 = DM, 1 = stars; mass already in Msun; id may be
+ *   null (the particle index is reported instead).
+ * halma_snapshot_gather: gas = one particle at the centre of every cell that is strictly
+ *   inside the box [c - R, c + R]^3, flagged by cr0amr and solapst, and at distance < R; mass
+ *   = (1 + delta) * rho_B * res^3 * mass_scale (mass_scale = rete**3, halo_gas.py:246),
+ *   velocity * 3e5; ascending patch, then ix, iy, iz -- bit-identical to the reference's
+ *   float64 arrays.  DM / stars = particles with squared distance <= R^2, ASCENDING index (the
+ *   reference's KD-tree returns the same set in tree order).  counts3 = n_gas, n_dm, n_star.
+ * halma_snapshot_fetch: copies the last gather's result to host arrays: gas8 = x, y, z, vx,
+ *   vy, vz, mass, temp; dm4 / st4 = x, y, z, mass; st_id = star ids.  Any pointer may be null.
+ * ------------------------------------------------------------------------------------ */
+typedef struct halma_snapshot halma_snapshot;
+int halma_snapshot_create(int device, double L, int32_t ncoarse, int64_t n_patch, const int32_t *level,
+                          const int32_t *nx, const int32_t *ny, const int32_t *nz, const double *rx,
+                          const double *ry, const double *rz, halma_snapshot **out);
+void halma_snapshot_destroy(halma_snapshot *snap);
+int64_t halma_snapshot_cells(const halma_snapshot *snap);
+int halma_snapshot_upload_patch(halma_snapshot *snap, int64_t patch, const float *delta, const float *vx,
+                                const float *vy, const float *vz, const float *temp, const uint8_t *cr0amr,
+                                const uint8_t *solapst);
+int halma_snapshot_upload_particles(halma_snapshot *snap, int kind, int64_t n, const double *x, const double *y,
+                                    const double *z, const double *mass, const int64_t *id);
+int halma_snapshot_gather(halma_snapshot *snap, double cx, double cy, double cz, double R, double rho_B,
+                          double mass_scale, int64_t *counts3);
+int halma_snapshot_fetch(halma_snapshot *snap, double *const *gas8, double *const *dm4, double *const *st4,
+                         int64_t *st_id);
+
+/* ------------------------------------------------------------------------------------ *
  * Pipe-rate microbenchmark used for the roofline denominator: measures
  * MUFU.RSQ, FFMA and packed FFMA2 issue rates per SM per clock, and the SM clock during
  * the measurement.  out: double[8] = {rsq_per_clk_sm, ffma_per_clk_sm, ffma2_per_clk_sm,

@@ -71,7 +71,10 @@ def patch_to_particles(patch_res, patch_rx, patch_ry, patch_rz, patch_nx, patch_
             & np.asarray(patch_cr0amr).astype(bool) & np.asarray(patch_solapst).astype(bool))
     ix, iy, iz = np.nonzero(keep)                        # C order = the reference's loop nest
     f64 = np.float64
-    mass = (1 + np.asarray(patch_delta)[ix, iy, iz].astype(f64)) * rho_B * patch_res ** 3        # :48
+    # :48.  numba lowers `patch_res**3` to patch_res*patch_res*patch_res (checked against numba
+    # 0.65 on random values: never pow()), and evaluates the product left to right.
+    res3 = patch_res * patch_res * patch_res
+    mass = (1 + np.asarray(patch_delta)[ix, iy, iz].astype(f64)) * rho_B * res3
     return (x[ix], y[iy], z[iz], np.asarray(patch_vx)[ix, iy, iz].astype(f64),
             np.asarray(patch_vy)[ix, iy, iz].astype(f64), np.asarray(patch_vz)[ix, iy, iz].astype(f64), mass,
             np.asarray(patch_temp)[ix, iy, iz].astype(f64))

@@ -24,6 +24,8 @@ EXPORTS = (
     "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join", "halma_comm_create", "halma_comm_destroy", "halma_plan_use_comm",
     "halma_plan_run", "halma_plan_download", "halma_unbind_halo", "halma_microbench",
     "halma_halo_shape_f32", "halma_sigma_projections_f32",
+    "halma_snapshot_create", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_snapshot_upload_patch",
+    "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_fetch",
 )
 
 
@@ -99,10 +101,19 @@ def lib() -> C.CDLL:
     L.halma_microbench.argtypes = [i32, f64p]
     L.halma_halo_shape_f32.argtypes = [i32, vp, vp, vp, vp, i64, vp]
     L.halma_sigma_projections_f32.argtypes = ([i32, i64, vp, C.c_int32, vp, i64] + [vp] * 7 + [C.c_float] * 7 + [vp])
+    L.halma_snapshot_create.argtypes = [i32, C.c_double, C.c_int32, i64] + [vp] * 7 + [C.POINTER(vp)]
+    L.halma_snapshot_destroy.argtypes = [vp]
+    L.halma_snapshot_destroy.restype = None
+    L.halma_snapshot_cells.argtypes = [vp]
+    L.halma_snapshot_cells.restype = i64
+    L.halma_snapshot_upload_patch.argtypes = [vp, i64] + [vp] * 7
+    L.halma_snapshot_upload_particles.argtypes = [vp, i32, i64] + [vp] * 5
+    L.halma_snapshot_gather.argtypes = [vp] + [C.c_double] * 6 + [vp]
+    L.halma_snapshot_fetch.argtypes = [vp] * 5
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("halma_last_error", "halma_potential_workspace_bytes", "halma_plan_destroy",
-                        "halma_comm_destroy"):
+                        "halma_comm_destroy", "halma_snapshot_destroy", "halma_snapshot_cells"):
             fn.restype = i32
     if L.halma_abi_version() != 1:
         raise ImportError("libhalma_unbind ABI version mismatch")

@@ -1,0 +1,165 @@
+"""Device-resident snapshot and the per-halo gather.
+
+Host-side mirror of the reference's gather step, python_scripts/halo_gas.py:
+  AMRgrid_to_particles          :56-141   (with patch_to_particles, :9-52)
+  st_gas_dm_particles_inside    :223-277  (with parallel_inside, :216-218, and the KD-tree
+                                           ball queries :255, :269)
+The reference walks the AMR patches in Python for every halo.  Here the whole snapshot --
+cell fields of every patch, DM and star particles -- is uploaded to HBM once (`Snapshot`)
+and each halo is one `halma_snapshot_gather` call on the device.  Gas arrays come back
+bit-identical to the reference's float64 arrays and in its order; DM and stars come back as
+the same set in ascending index order (the reference's KD-tree order is unspecified).
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+def create_vector_levels(npatch) -> np.ndarray:
+    """Level of every patch, index 0 = the base grid (masclet_framework.tools.create_vector_levels,
+    called at halo_gas.py:92): [0] + [l] * npatch[l] for l >= 1."""
+    out = [np.zeros(1, dtype=np.int32)]
+    for lev in range(1, len(npatch)):
+        out.append(np.full(int(npatch[lev]), lev, dtype=np.int32))
+    return np.concatenate(out)
+
+
+def _c_f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)          # C order: ix slowest, like the loop nest at :30-38
+
+
+def _c_u8(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a) != 0, dtype=np.uint8)
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Snapshot:
+    """One simulation output resident on the GPU: AMR hierarchy + gas cell fields, and
+    optionally the DM and star particles."""
+
+    def __init__(self, L, ncoarse, grid_data, gas_data, masclet_dm_data=None, masclet_st_data=None, *,
+                 mass_to_sun: float = 1.0, device: int = 0):
+        npatch = grid_data[5]
+        level = create_vector_levels(npatch)
+        n_patch = len(level)
+        nx, ny, nz = (np.ascontiguousarray(grid_data[k][:n_patch], dtype=np.int32) for k in (6, 7, 8))
+        rx, ry, rz = (_f64(grid_data[k][:n_patch]) for k in (12, 13, 14))
+        if not (len(nx) == len(ny) == len(nz) == len(rx) == len(ry) == len(rz) == n_patch):
+            raise ValueError("grid_data arrays are shorter than 1 + sum(npatch)")
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.device = device
+        self.n_patch = n_patch
+        _lib.check(self._L.halma_snapshot_create(device, float(L), int(ncoarse), n_patch, level.ctypes.data,
+                                                 nx.ctypes.data, ny.ctypes.data, nz.ctypes.data, rx.ctypes.data,
+                                                 ry.ctypes.data, rz.ctypes.data, C.byref(self._h)))
+        delta, vx, vy, vz, temp, cr0amr, solapst = (gas_data[k] for k in range(7))
+        for p in range(1, n_patch):
+            shape = (int(nx[p]), int(ny[p]), int(nz[p]))
+            arrs = [_c_f32(a[p]) for a in (delta, vx, vy, vz, temp)] + [_c_u8(cr0amr[p]), _c_u8(solapst[p])]
+            for a in arrs:
+                if a.shape != shape:
+                    raise ValueError("patch %d: field of shape %s, grid says %s" % (p, a.shape, shape))
+            _lib.check(self._L.halma_snapshot_upload_patch(self._h, p, *[a.ctypes.data for a in arrs]))
+        self.n_cells = int(self._L.halma_snapshot_cells(self._h))
+        self.oripa_dtype = np.int64
+        if masclet_dm_data is not None:
+            self.upload_particles(0, masclet_dm_data[0], masclet_dm_data[1], masclet_dm_data[2],
+                                  np.asarray(masclet_dm_data[3]) * mass_to_sun)                     # :252
+        if masclet_st_data is not None:
+            self.oripa_dtype = np.asarray(masclet_st_data[9]).dtype
+            self.upload_particles(1, masclet_st_data[0], masclet_st_data[1], masclet_st_data[2],
+                                  np.asarray(masclet_st_data[6]) * mass_to_sun, masclet_st_data[9])  # :265-266
+
+    def upload_particles(self, kind: int, x, y, z, mass, ids=None) -> None:
+        x, y, z, mass = map(_f64, (x, y, z, mass))
+        if not (len(x) == len(y) == len(z) == len(mass)):
+            raise ValueError("particle arrays differ in length")
+        idp = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            if len(ids) != len(x):
+                raise ValueError("ids differ in length from the positions")
+            idp = ids.ctypes.data
+        _lib.check(self._L.halma_snapshot_upload_particles(self._h, kind, len(x), x.ctypes.data, y.ctypes.data,
+                                                           z.ctypes.data, mass.ctypes.data, idp))
+
+    def gather(self, cx, cy, cz, R, rho_B, rete=1.0, *, gas=True, dm=True, stars=True):
+        """Returns the 17-tuple of st_gas_dm_particles_inside (halo_gas.py:276-277); classes that
+        are switched off come back empty."""
+        counts = (C.c_int64 * 3)()
+        _lib.check(self._L.halma_snapshot_gather(self._h, float(cx), float(cy), float(cz), float(R), float(rho_B),
+                                                 float(rete) ** 3, counts))
+        ng, nd, ns = (int(c) for c in counts)
+        g = [np.empty(ng if gas else 0) for _ in range(8)]
+        d = [np.empty(nd if dm else 0) for _ in range(4)]
+        s = [np.empty(ns if stars else 0) for _ in range(4)]
+        sid = np.empty(ns if stars else 0, dtype=np.int64)
+
+        def ptrs(arrs, on):
+            return (C.c_void_p * len(arrs))(*[a.ctypes.data if on else None for a in arrs])
+
+        _lib.check(self._L.halma_snapshot_fetch(self._h, ptrs(g, gas and ng), ptrs(d, dm and nd), ptrs(s, stars and ns),
+                                                sid.ctypes.data if stars and ns else None))
+        return (*g, *d, *s, sid.astype(self.oripa_dtype, copy=False))
+
+    def close(self) -> None:
+        if self._h:
+            self._L.halma_snapshot_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+# The reference passes the same snapshot objects for every halo of a snapshot (pyHALMA.py:930-1037);
+# keep the device copy of the last one seen.  The strong references keep id() from being reused.
+_cache: dict = {"key": None, "refs": None, "snap": None}
+
+
+def snapshot_for(L, ncoarse, grid_data, gas_data, masclet_dm_data, masclet_st_data, mass_to_sun, device) -> Snapshot:
+    key = (id(grid_data), id(gas_data), id(masclet_dm_data), id(masclet_st_data), float(L), int(ncoarse),
+           float(mass_to_sun), int(device))
+    if _cache["key"] != key:
+        if _cache["snap"] is not None:
+            _cache["snap"].close()
+        _cache.update(key=None, refs=None, snap=None)
+        snap = Snapshot(L, ncoarse, grid_data, gas_data, masclet_dm_data, masclet_st_data, mass_to_sun=mass_to_sun,
+                        device=device)
+        _cache.update(key=key, refs=(grid_data, gas_data, masclet_dm_data, masclet_st_data), snap=snap)
+    return _cache["snap"]
+
+
+def release_cached_snapshot() -> None:
+    if _cache["snap"] is not None:
+        _cache["snap"].close()
+    _cache.update(key=None, refs=None, snap=None)
+
+
+def default_mass_to_sun() -> float:
+    """masclet_framework.units.mass_to_sun (halo_gas.py:252,265) when that un-vendored package is
+    importable; callers without it pass mass_to_sun explicitly."""
+    try:
+        from masclet_framework import units      # type: ignore
+    except Exception as exc:
+        raise ImportError("masclet_framework is not importable: pass mass_to_sun=... (masses are multiplied by "
+                          "units.mass_to_sun at halo_gas.py:252,265)") from exc
+    return float(units.mass_to_sun)

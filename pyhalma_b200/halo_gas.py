@@ -7,6 +7,8 @@ like calls into the reference:
   serial_brute_force_binding_energy_fortran   halo_gas.py:191-215
   RPS                                         halo_gas.py:285-492
   most_bound_particle                         halo_gas.py:498-634
+  AMRgrid_to_particles                        halo_gas.py:56-141   (the gather before the path,
+  st_gas_dm_particles_inside                  halo_gas.py:223-277   SURVEY.md §8f-3)
 
 All potential sums run on the GPU through libhalma_unbind (no CPU fallback).  The
 Monte-Carlo subsampling above BRUTE_FORCE_LIM (halo_gas.py:306-321 and seven more sites)
@@ -17,7 +19,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _lib
+from . import _lib, gather
 from .particle import particle
 from .unbind import G_CONST, UnbindPlan
 
@@ -173,8 +175,41 @@ def most_bound_particle(gas_x, gas_y, gas_z, gas_mass, dm_x, dm_y, dm_z, dm_mass
     return st_x[k], st_y[k], st_z[k], st_oripa[k]
 
 
-def AMRgrid_to_particles(*args, **kwargs):  # noqa: N802
-    """python_scripts/halo_gas.py:56-141 (AMR cells -> pseudo-particles) is the step before
-    the hot path and needs MASCLET files + the un-vendored masclet_framework (SURVEY.md §2
-    row 7).  Callers bind their own gather here."""
-    raise NotImplementedError("AMRgrid_to_particles is outside the replaced hot path")
+def AMRgrid_to_particles(L, ncoarse, grid_data, gas_data, Rrps, cx, cy, cz, rho_B, *, device=0):  # noqa: N802
+    """python_scripts/halo_gas.py:56-141: the gas cells (level >= 1, not refined, not overlapped)
+    whose centres lie strictly inside the box of half-width Rrps, as pseudo-particles
+    x, y, z, vx, vy, vz (km/s), mass (comoving: no rete**3 yet), temp -- float64, in the
+    reference's order.  The snapshot is uploaded on first use and stays on the GPU."""
+    snap = gather.snapshot_for(L, ncoarse, grid_data, gas_data, None, None, 1.0, device)
+    return _box_gas(snap, cx, cy, cz, Rrps, rho_B)
+
+
+def _box_gas(snap, cx, cy, cz, Rrps, rho_B):
+    # the device selects box AND sphere (:236 follows :233 at the only call site); the box alone is
+    # inside the sphere of radius sqrt(3)*Rrps, so ask for a slightly larger sphere and clip to the box here
+    out = snap.gather(cx, cy, cz, Rrps * 1.75, rho_B, 1.0, dm=False, stars=False)[:8]
+    x, y, z = out[0], out[1], out[2]
+    keep = ((x > cx - Rrps) & (x < cx + Rrps) & (y > cy - Rrps) & (y < cy + Rrps) & (z > cz - Rrps)
+            & (z < cz + Rrps))
+    return tuple(a[keep] for a in out)
+
+
+def parallel_inside(array_x, array_y, array_z, R, cx, cy, cz):
+    """python_scripts/halo_gas.py:216-218."""
+    return np.sqrt((array_x - cx) ** 2 + (array_y - cy) ** 2 + (array_z - cz) ** 2) < R
+
+
+def st_gas_dm_particles_inside(rete, L, ncoarse, grid_data, gas_data, masclet_dm_data, masclet_st_data,
+                               st_kdtree, dm_kdtree, cx, cy, cz, R, rho_B, *, mass_to_sun=None, device=0):
+    """python_scripts/halo_gas.py:223-277, same arguments and the same 17-tuple:
+    gas x, y, z, vx, vy, vz, mass (x rete**3), temp; DM x, y, z, mass; stars x, y, z, mass, oripa.
+    One device call per halo against the resident snapshot.  The KD-trees are accepted for
+    signature compatibility and not used: the ball query is a brute-force pass over the
+    resident particles (24 B per particle at HBM speed).  Gas is bit-identical to the
+    reference; DM and stars are the same set in ascending index order."""
+    del st_kdtree, dm_kdtree
+    if mass_to_sun is None:
+        mass_to_sun = gather.default_mass_to_sun()
+    snap = gather.snapshot_for(L, ncoarse, grid_data, gas_data, masclet_dm_data, masclet_st_data, mass_to_sun,
+                               device)
+    return snap.gather(cx, cy, cz, R, rho_B, rete)

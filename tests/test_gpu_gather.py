@@ -1,0 +1,100 @@
+"""GPU parity of the gather step through the C-ABI: bit-exact against the
+fixture written by the reference's own st_gas_dm_particles_inside and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gather as OG
+from pyhalma_b200 import gather, halo_gas, synth
+from test_oracle_gather import SNAP_KW, check_against_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def snap():
+    return synth.amr_snapshot(**SNAP_KW)
+
+
+def call(s, cx, cy, cz, R, fn=halo_gas.st_gas_dm_particles_inside, **kw):
+    return fn(s.rete, s.L, s.ncoarse, s.grid_data, s.gas_data, s.masclet_dm_data, s.masclet_st_data, None, None,
+              cx, cy, cz, R, s.rho_B, **kw)
+
+
+def test_gather_golden_bit_exact(snap, golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, "gather_amr.npz")))
+    for tag in g["tags"]:
+        cx, cy, cz, R = g[tag + "_args"]
+        out = call(snap, cx, cy, cz, R, mass_to_sun=1.0)
+        assert len(out) == 17
+        check_against_golden(out, g, tag)
+        # DM and stars ascending in the input index
+        assert np.all(np.diff(out[16]) > 0)
+
+
+def test_gather_random_queries_against_oracle(snap):
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        c = np.asarray(snap.centre) + rng.normal(0, 0.01, 3)
+        R = float(10 ** rng.uniform(-3.3, -0.8))
+        got = call(snap, *c, R, mass_to_sun=1.0)
+        want = call(snap, *c, R, fn=OG.st_gas_dm_particles_inside)
+        for n, a, b in zip(OG.GATHER_NAMES, got, want):
+            assert a.dtype == b.dtype, n
+            np.testing.assert_array_equal(a, b, err_msg=n)      # same order too: both ascending
+    # mass_to_sun scales DM and star masses only (halo_gas.py:252,265)
+    a = call(snap, *snap.centre, 0.02, mass_to_sun=1.0)
+    b = call(snap, *snap.centre, 0.02, mass_to_sun=2.0)
+    np.testing.assert_array_equal(b[11], 2.0 * a[11])
+    np.testing.assert_array_equal(b[15], 2.0 * a[15])
+    np.testing.assert_array_equal(b[6], a[6])
+    gather.release_cached_snapshot()
+
+
+def test_amrgrid_to_particles_box_only(snap):
+    cx, cy, cz = snap.centre
+    for R in (0.004, 0.03):
+        got = halo_gas.AMRgrid_to_particles(snap.L, snap.ncoarse, snap.grid_data, snap.gas_data, R, cx, cy, cz, snap.rho_B)
+        want = OG.AMRgrid_to_particles(snap.L, snap.ncoarse, snap.grid_data, snap.gas_data, R, cx, cy, cz, snap.rho_B)
+        assert len(want[0]) > 0
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    gather.release_cached_snapshot()
+
+
+def test_snapshot_object_edge_cases(snap):
+    with gather.Snapshot(snap.L, snap.ncoarse, snap.grid_data, snap.gas_data) as s:     # no particles uploaded
+        assert s.n_cells == snap.n_cells
+        out = s.gather(*snap.centre, 0.02, snap.rho_B, snap.rete)
+        assert len(out[0]) > 0 and len(out[8]) == 0 and len(out[12]) == 0
+        far = s.gather(100.0, 100.0, 100.0, 0.02, snap.rho_B, snap.rete)                # nothing there
+        assert all(len(a) == 0 for a in far)
+        zero = s.gather(*snap.centre, 0.0, snap.rho_B, snap.rete)
+        assert all(len(a) == 0 for a in zero)
+        s.upload_particles(1, [snap.centre[0]], [snap.centre[1]], [snap.centre[2]], [5.0], [42])
+        one = s.gather(*snap.centre, 0.0, snap.rho_B, snap.rete)                        # distance 0 <= R = 0
+        assert list(one[16]) == [42] and one[15][0] == 5.0
+        with pytest.raises(ValueError):
+            s.upload_particles(0, [0.0, 1.0], [0.0], [0.0], [1.0])
+    # a grid whose fields disagree with the declared extents is refused
+    bad = [list(a) for a in snap.gas_data]
+    bad[0][1] = bad[0][1][:-1]
+    with pytest.raises(ValueError):
+        gather.Snapshot(snap.L, snap.ncoarse, snap.grid_data, bad)
+    with pytest.raises(ImportError):
+        call(snap, *snap.centre, 0.01)            # masclet_framework absent and no mass_to_sun given
+
+
+def test_gather_feeds_rps_like_the_reference_pipeline(snap):
+    """pyHALMA.py:1027-1054: gather, then RPS on the gathered arrays; the same through the oracle."""
+    from oracle import oracle as O
+    cx, cy, cz = snap.centre
+    R = 0.012
+    got = call(snap, cx, cy, cz, R, mass_to_sun=1.0)
+    want = call(snap, cx, cy, cz, R, fn=OG.st_gas_dm_particles_inside)
+    vb = synth.BULK_V
+    a = halo_gas.RPS(*got[:16], *vb, 10 ** 9, 8e7, 1, mode="exact")
+    b = O.RPS(*want[:16], *vb, 10 ** 9, 8e7, 1)
+    np.testing.assert_array_equal(np.array(a), np.array(b.as_tuple()))
+    gather.release_cached_snapshot()
