@@ -264,6 +264,10 @@ int halma_sigma_projections_f32(int device, int64_t npart, const float *grid, in
  * halma_snapshot_fetch: copies the last gather's result to host arrays: gas8 = x, y, z, vx,
  *   vy, vz, mass, temp; dm4 / st4 = x, y, z, mass; st_id = star ids.  Any pointer may be null.
  * ------------------------------------------------------------------------------------ */
+/* CUDA-event time (ms) of the kernels of the last halma_halo_shape_f32 /
+ * halma_sigma_projections_f32 / halma_snapshot_gather call made on this thread. */
+double halma_last_kernel_ms(void);
+
 typedef struct halma_snapshot halma_snapshot;
 int halma_snapshot_create(int device, double L, int32_t ncoarse, int64_t n_patch, const int32_t *level,
                           const int32_t *nx, const int32_t *ny, const int32_t *nz, const double *rx,

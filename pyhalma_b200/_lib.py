@@ -25,7 +25,7 @@ EXPORTS = (
     "halma_plan_run", "halma_plan_download", "halma_unbind_halo", "halma_microbench",
     "halma_halo_shape_f32", "halma_sigma_projections_f32",
     "halma_snapshot_create", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_snapshot_upload_patch",
-    "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_fetch",
+    "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_fetch", "halma_last_kernel_ms",
 )
 
 
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.halma_snapshot_destroy.restype = None
     L.halma_snapshot_cells.argtypes = [vp]
     L.halma_snapshot_cells.restype = i64
+    L.halma_last_kernel_ms.restype = C.c_double
     L.halma_snapshot_upload_patch.argtypes = [vp, i64] + [vp] * 7
     L.halma_snapshot_upload_particles.argtypes = [vp, i32, i64] + [vp] * 5
     L.halma_snapshot_gather.argtypes = [vp] + [C.c_double] * 6 + [vp]
@@ -113,7 +114,7 @@ def lib() -> C.CDLL:
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("halma_last_error", "halma_potential_workspace_bytes", "halma_plan_destroy",
-                        "halma_comm_destroy", "halma_snapshot_destroy", "halma_snapshot_cells"):
+                        "halma_comm_destroy", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_last_kernel_ms"):
             fn.restype = i32
     if L.halma_abi_version() != 1:
         raise ImportError("libhalma_unbind ABI version mismatch")

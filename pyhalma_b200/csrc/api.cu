@@ -106,6 +106,12 @@ int halma_internal_ctx(int device, int *sm_count, cudaStream_t *stream)
 }
 int halma_internal_fail(int code, const char *msg) { return fail(code, msg); }
 
+// CUDA-event time of the kernels of the last halo_shape / sigma_projections / snapshot call on
+// this thread (their entry points take host buffers, so wall time would mostly measure PCIe).
+static thread_local double g_last_kernel_ms = 0.0;
+void halma_internal_set_kernel_ms(double ms) { g_last_kernel_ms = ms; }
+extern "C" double halma_last_kernel_ms(void) { return g_last_kernel_ms; }
+
 extern "C" int halma_device_count(int *count)
 {
     if (!count) return fail(HALMA_ERR_INVALID, "count is null");

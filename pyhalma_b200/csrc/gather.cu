@@ -24,6 +24,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/halma_unbind.h"
+#include "aux_timer.h"
 #include "halma_common.cuh"
 
 int halma_internal_ctx(int device, int *sm_count, cudaStream_t *stream);
@@ -467,6 +468,7 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
     q.R2 = R * R;
     q.mass_factor[0] = rho_B;
     q.mass_factor[1] = mass_scale;
+    KernelTimer timer(s->stream);
     // ---- gas cells ----
     if (s->pd_dirty) {
         for (int64_t p = 0; p < s->n_patch; ++p) s->host_pd[p].active = s->host_pd[p].res != 0.0 && s->uploaded[p];
@@ -534,7 +536,9 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
         });
         if (rc) return rc;
     }
+    timer.stop();
     GA_TRY(cudaStreamSynchronize(s->stream));
+    timer.publish();
     for (int k = 0; k < 3; ++k) counts3[k] = s->n_out[k];
     s->have_result = true;
     return HALMA_OK;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/halma_unbind.h"
+#include "aux_timer.h"
 #include "halma_common.cuh"
 
 int halma_internal_ctx(int device, int *sm_count, cudaStream_t *stream);
@@ -45,24 +46,57 @@ __device__ __forceinline__ void block_sum_atomic(double (&v)[NV], double *out)
     }
 }
 
-// particle_subroutines.f90:188-199: sum m r_i r_j (upper triangle) and sum m
+// particle_subroutines.f90:188-199: sum m r_i r_j (upper triangle) and sum m.
+// The four arrays start on 16-byte boundaries (the host pads the stride): 128-bit loads, four
+// particles per thread and trip, 64 B in flight per thread.
+__device__ __forceinline__ void inertia_add(double (&s)[7], float mf, float xf, float yf, float zf)
+{
+    const double mx = mf, a = xf, b = yf, c = zf;
+    s[0] += mx * a * a;
+    s[1] += mx * a * b;
+    s[2] += mx * a * c;
+    s[3] += mx * b * b;
+    s[4] += mx * b * c;
+    s[5] += mx * c * c;
+    s[6] += mx;
+}
+
 __global__ void __launch_bounds__(kShBlock) k_inertia(const float *__restrict__ x, const float *__restrict__ y,
                                                       const float *__restrict__ z, const float *__restrict__ m,
                                                       int64_t n, double *out7)
 {
     double s[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+    const int64_t n4 = n >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x), *y4 = reinterpret_cast<const float4 *>(y),
+                 *z4 = reinterpret_cast<const float4 *>(z), *m4 = reinterpret_cast<const float4 *>(m);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const double mx = static_cast<double>(m[i]), a = x[i], b = y[i], c = z[i];
-        s[0] += mx * a * a;
-        s[1] += mx * a * b;
-        s[2] += mx * a * c;
-        s[3] += mx * b * b;
-        s[4] += mx * b * c;
-        s[5] += mx * c * c;
-        s[6] += mx;
+        const float4 a = x4[i], b = y4[i], c = z4[i], w = m4[i];
+        inertia_add(s, w.x, a.x, b.x, c.x);
+        inertia_add(s, w.y, a.y, b.y, c.y);
+        inertia_add(s, w.z, a.z, b.z, c.z);
+        inertia_add(s, w.w, a.w, b.w, c.w);
     }
-    block_sum_atomic<7>(s, out7);
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n4 << 2) + threadIdx.x;
+        inertia_add(s, m[i], x[i], y[i], z[i]);
+    }
+    // one partial per block, summed on the host in block order: bit-reproducible
+    __shared__ double red[7][kShBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        double v = s[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[k][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double v = 0.0;
+        for (int w = 0; w < kShBlock / 32; ++w) v += red[threadIdx.x][w];
+        out7[blockIdx.x * 7 + threadIdx.x] = v;
+    }
 }
 
 struct SigmaParams {
@@ -72,8 +106,15 @@ struct SigmaParams {
     int64_t npart;
     int32_t n_cell;
     float cx, cy, cz, r05[3];
-    double *vcm[3], *sd[3], *sig[3];
+    double *vcm[3], *sd[3], *sig[3];     // final maps
     int32_t *cnt[3];
+    // Replicated accumulation targets: block b adds into replica (b & rep_mask), so the float64
+    // atomics of different blocks mostly hit different L2 lines (scripts/probes/atomic_hist_probe.cu:
+    // 4.6 G updates/s with one copy of a 25 x 25 map, 94 G/s with 64); k_fold sums the replicas.
+    double *racc;           // replica r: racc + r * 6 n^2: vcm x3 | sd x3 (pass 1), sig x3 (pass 2)
+    int32_t *rcnt;          // replica r: rcnt + r * 3 n^2
+    int32_t rep_mask;
+    int32_t grid_sorted;    // grid is strictly increasing and free of NaN: binary search
     int16_t *cell;          // 3 per listed particle
     double *s05;            // 3 sums
     int32_t *c05;           // 3 counters
@@ -94,6 +135,36 @@ __device__ __forceinline__ int nearest_cell(const float *sgrid, int n_cell, floa
     return best;
 }
 
+// The same for a strictly increasing grid (checked on the host; pyHALMA.py:1001 builds it with
+// np.arange): |grid - d| falls, then rises, so the first minimum is next to the first grid
+// point >= d; a plateau of equal rounded differences to its left is walked back so the
+// result is the linear scan's in every case.
+__device__ __forceinline__ int nearest_cell_sorted(const float *sgrid, int n_cell, float d)
+{
+    int lo = 0, hi = n_cell;                 // first k with grid[k] >= d
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sgrid[mid] < d)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    int best = lo > 0 ? lo - 1 : 0;
+    float bv = fabsf(sgrid[best] - d);
+    if (lo < n_cell && lo != best) {
+        const float v = fabsf(sgrid[lo] - d);
+        if (v < bv) {
+            bv = v;
+            best = lo;
+        }
+    }
+    while (best > 0 && fabsf(sgrid[best - 1] - d) <= bv) {
+        --best;
+        bv = fabsf(sgrid[best] - d);
+    }
+    return best;
+}
+
 // pass 1 (:264-281): cell of every listed particle, mass-weighted velocity, mass and count maps
 __global__ void __launch_bounds__(kShBlock) k_sigma_bin(const SigmaParams p)
 {
@@ -101,12 +172,23 @@ __global__ void __launch_bounds__(kShBlock) k_sigma_bin(const SigmaParams p)
     for (int k = threadIdx.x; k < p.n_cell; k += blockDim.x) sgrid[k] = p.grid[k];
     __syncthreads();
     const int nc = p.n_cell;
+    const size_t nn = static_cast<size_t>(nc) * nc;
+    double *acc = p.racc + (blockIdx.x & p.rep_mask) * (6 * nn);
+    int32_t *cnt = p.rcnt + (blockIdx.x & p.rep_mask) * (3 * nn);
     for (int64_t ip = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; ip < p.npart;
          ip += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t q = p.part_list[ip];
-        const int ix = nearest_cell(sgrid, nc, p.x[q] - p.cx);
-        const int iy = nearest_cell(sgrid, nc, p.y[q] - p.cy);
-        const int iz = nearest_cell(sgrid, nc, p.z[q] - p.cz);
+        const float dx = p.x[q] - p.cx, dy = p.y[q] - p.cy, dz = p.z[q] - p.cz;
+        int ix, iy, iz;
+        if (p.grid_sorted && dx == dx && dy == dy && dz == dz) {
+            ix = nearest_cell_sorted(sgrid, nc, dx);
+            iy = nearest_cell_sorted(sgrid, nc, dy);
+            iz = nearest_cell_sorted(sgrid, nc, dz);
+        } else {
+            ix = nearest_cell(sgrid, nc, dx);
+            iy = nearest_cell(sgrid, nc, dy);
+            iz = nearest_cell(sgrid, nc, dz);
+        }
         p.cell[3 * ip] = static_cast<int16_t>(ix);
         p.cell[3 * ip + 1] = static_cast<int16_t>(iy);
         p.cell[3 * ip + 2] = static_cast<int16_t>(iz);
@@ -116,10 +198,22 @@ __global__ void __launch_bounds__(kShBlock) k_sigma_bin(const SigmaParams p)
         const double v3[3] = {p.vx[q], p.vy[q], p.vz[q]};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicAdd(&p.vcm[a][k3[a]], v3[a] * m);
-            atomicAdd(&p.sd[a][k3[a]], m);
-            atomicAdd(&p.cnt[a][k3[a]], 1);
+            atomicAdd(&acc[a * nn + k3[a]], v3[a] * m);
+            atomicAdd(&acc[(3 + a) * nn + k3[a]], m);
+            atomicAdd(&cnt[a * nn + k3[a]], 1);
         }
+    }
+}
+
+// dst[k] = sum over replicas, in replica order
+template <class T>
+__global__ void k_fold(T *__restrict__ dst, const T *__restrict__ src, int64_t n, int reps, int64_t stride)
+{
+    for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
+         k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        T v = 0;
+        for (int r = 0; r < reps; ++r) v += src[r * stride + k];
+        dst[k] = v;
     }
 }
 
@@ -141,6 +235,8 @@ __global__ void k_sigma_maps(double *a, const double *den_d, const int32_t *den_
 __global__ void __launch_bounds__(kShBlock) k_sigma_dev(const SigmaParams p)
 {
     const int nc = p.n_cell;
+    const size_t nn = static_cast<size_t>(nc) * nc;
+    double *acc = p.racc + (blockIdx.x & p.rep_mask) * (6 * nn);
     for (int64_t ip = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; ip < p.npart;
          ip += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t q = p.part_list[ip];
@@ -151,7 +247,7 @@ __global__ void __launch_bounds__(kShBlock) k_sigma_dev(const SigmaParams p)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const double d = v3[a] - p.vcm[a][k3[a]];
-            atomicAdd(&p.sig[a][k3[a]], d * d);
+            atomicAdd(&acc[a * nn + k3[a]], d * d);
         }
     }
 }
@@ -282,19 +378,25 @@ extern "C" int halma_halo_shape_f32(int device, const float *x, const float *y, 
     if (npart > 0) {
         float *d = nullptr;
         double *d7 = nullptr;
-        const size_t n = static_cast<size_t>(npart);
+        const size_t n = (static_cast<size_t>(npart) + 3) & ~size_t(3);      // stride: 16-byte aligned arrays
+        const int blocks = static_cast<int>(std::min<int64_t>((npart / 4 + kShBlock) / kShBlock, sm * 8));
+        std::vector<double> part(static_cast<size_t>(blocks) * 7);
         SH_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d), 4 * n * sizeof(float), s));
-        SH_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d7), 7 * sizeof(double), s));
+        SH_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d7), part.size() * sizeof(double), s));
         const float *src[4] = {x, y, z, mass};
-        for (int k = 0; k < 4; ++k) SH_TRY(cudaMemcpyAsync(d + k * n, src[k], n * sizeof(float), cudaMemcpyHostToDevice, s));
-        SH_TRY(cudaMemsetAsync(d7, 0, 7 * sizeof(double), s));
-        const int blocks = static_cast<int>(std::min<int64_t>((npart + kShBlock - 1) / kShBlock, sm * 8));
+        for (int k = 0; k < 4; ++k)
+            SH_TRY(cudaMemcpyAsync(d + k * n, src[k], npart * sizeof(float), cudaMemcpyHostToDevice, s));
+        KernelTimer timer(s);
         k_inertia<<<blocks, kShBlock, 0, s>>>(d, d + n, d + 2 * n, d + 3 * n, npart, d7);
+        timer.stop();
         SH_TRY(cudaGetLastError());
-        SH_TRY(cudaMemcpyAsync(h7, d7, sizeof h7, cudaMemcpyDeviceToHost, s));
+        SH_TRY(cudaMemcpyAsync(part.data(), d7, part.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
         SH_TRY(cudaFreeAsync(d, s));
         SH_TRY(cudaFreeAsync(d7, s));
         SH_TRY(cudaStreamSynchronize(s));
+        timer.publish();
+        for (int b = 0; b < blocks; ++b)
+            for (int k = 0; k < 7; ++k) h7[k] += part[static_cast<size_t>(b) * 7 + k];
     }
     // :203 normalise, :206-211 eigenvalues, largest first, square roots
     const double M = h7[6];
@@ -336,6 +438,14 @@ extern "C" int halma_sigma_projections_f32(int device, int64_t npart, const floa
     SH_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_cell), 3 * np * sizeof(int16_t), s));
     SH_TRY(cudaMemsetAsync(d_maps, 0, (9 * nn + 3) * sizeof(double), s));
     SH_TRY(cudaMemsetAsync(d_i, 0, (3 * nn + 3) * sizeof(int32_t), s));
+    int reps = 64;                                     // power of two, at most 2^22 map cells in all
+    while (reps > 1 && static_cast<size_t>(reps) * nn > (size_t(1) << 22)) reps >>= 1;
+    double *d_racc = nullptr;
+    int32_t *d_rcnt = nullptr;
+    SH_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_racc), reps * 6 * nn * sizeof(double), s));
+    SH_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_rcnt), reps * 3 * nn * sizeof(int32_t), s));
+    SH_TRY(cudaMemsetAsync(d_racc, 0, reps * 6 * nn * sizeof(double), s));
+    SH_TRY(cudaMemsetAsync(d_rcnt, 0, reps * 3 * nn * sizeof(int32_t), s));
     const float *src[7] = {st_x, st_y, st_z, st_vx, st_vy, st_vz, st_mass};
     if (n_all > 0)
         for (int k = 0; k < 7; ++k)
@@ -370,17 +480,30 @@ extern "C" int halma_sigma_projections_f32(int device, int64_t npart, const floa
     }
     p.s05 = d_maps + 9 * nn;
     p.c05 = d_i + 3 * nn;
+    p.racc = d_racc;
+    p.rcnt = d_rcnt;
+    p.rep_mask = reps - 1;
+    p.grid_sorted = 1;
+    for (int k = 1; k < n_cell; ++k)
+        if (!(grid[k] > grid[k - 1])) p.grid_sorted = 0;
+    if (!(grid[0] == grid[0])) p.grid_sorted = 0;
     p.cell = d_cell;
     const int pb = static_cast<int>(std::min<int64_t>((npart + kShBlock - 1) / kShBlock, sm * 8));
     const int mb = static_cast<int>(std::min<size_t>((nn + 255) / 256, static_cast<size_t>(sm) * 8));
+    KernelTimer timer(s);
     if (npart > 0) {
         k_sigma_bin<<<pb, kShBlock, n_cell * sizeof(float), s>>>(p);
+        k_fold<double><<<mb, 256, 0, s>>>(d_maps, d_racc, 6 * nn, reps, 6 * nn);          // vcm | sd
+        k_fold<int32_t><<<mb, 256, 0, s>>>(d_i, d_rcnt, 3 * nn, reps, 3 * nn);
         for (int a = 0; a < 3; ++a) k_sigma_maps<<<mb, 256, 0, s>>>(p.vcm[a], p.sd[a], nullptr, nn, 0);
+        SH_TRY(cudaMemsetAsync(d_racc, 0, reps * 6 * nn * sizeof(double), s));
         k_sigma_dev<<<pb, kShBlock, 0, s>>>(p);
+        k_fold<double><<<mb, 256, 0, s>>>(d_maps + 6 * nn, d_racc, 3 * nn, reps, 6 * nn);   // sig
         for (int a = 0; a < 3; ++a) k_sigma_maps<<<mb, 256, 0, s>>>(p.sig[a], nullptr, p.cnt[a], nn, 1);
         k_sigma_r05<<<pb, kShBlock, 0, s>>>(p);
         SH_TRY(cudaGetLastError());
     }
+    timer.stop();
     std::vector<double> maps(9 * nn + 3);
     int32_t c05[3];
     SH_TRY(cudaMemcpyAsync(maps.data(), d_maps, maps.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -388,8 +511,11 @@ extern "C" int halma_sigma_projections_f32(int device, int64_t npart, const floa
     SH_TRY(cudaFreeAsync(d_f, s));
     SH_TRY(cudaFreeAsync(d_maps, s));
     SH_TRY(cudaFreeAsync(d_i, s));
+    SH_TRY(cudaFreeAsync(d_racc, s));
+    SH_TRY(cudaFreeAsync(d_rcnt, s));
     SH_TRY(cudaFreeAsync(d_cell, s));
     SH_TRY(cudaStreamSynchronize(s));
+    timer.publish();
     // :356-366 means inside R05; :370-454 V/sigma and lambda_R per projection, then the average.
     // The map loops are n_cell^2 long: done here, in the reference's loop order.
     const double *vcm[3] = {maps.data(), maps.data() + nn, maps.data() + 2 * nn};

@@ -400,7 +400,7 @@ def amr_snapshot(n_levels: int = 5, patches_per_level: int = 3, n_dm: int = 20_0
         refined = np.zeros(shape, dtype=bool)
         overl = np.zeros(shape, dtype=bool)
         for q in range(1, npt):
-            if q == p or p == 0:
+            if q == p or p == 0 or level_of[q] not in (level_of[p], level_of[p] + 1):
                 continue
             inside = ((X > lo_edges[q][0]) & (X < hi_edges[q][0]) & (Y > lo_edges[q][1]) & (Y < hi_edges[q][1])
                       & (Z > lo_edges[q][2]) & (Z < hi_edges[q][2]))

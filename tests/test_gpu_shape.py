@@ -55,6 +55,12 @@ def test_sigma_projections_parity_and_errors():
         assert isinstance(got, tuple) and len(got) == 5 and all(isinstance(v, float) for v in got)
         np.testing.assert_allclose(got, O.sigma_projections(*args, wide=True), rtol=WIDE_RTOL)
         np.testing.assert_allclose(got, O.sigma_projections(*args), rtol=REF_RTOL * 10)
+    # grids that are not strictly increasing take the linear minloc scan
+    for grid in ((np.arange(25) - 12)[::-1] * ll, np.repeat((np.arange(13) - 6) * 2 * ll, 2)[:25],
+                 np.random.default_rng(4).permutation(25) * ll - 12 * ll):
+        args = (1, len(pl), grid, 25, pl + 1, x, y, z, vx, vy, vz, m, *c, *r05, ll)
+        np.testing.assert_allclose(particle.sigma_projections(*args), O.sigma_projections(*args, wide=True),
+                                   rtol=WIDE_RTOL)
     grid = np.array([-1.0, 0.0, 1.0])
     v = np.array([10.0, -10.0])
     xx = np.array([0.1, -0.1]); yy = np.array([0.05, 0.0]); zz = np.array([0.0, 0.1])
