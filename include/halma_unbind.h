@@ -166,7 +166,7 @@ int halma_plan_create(const halma_unbind_config *cfg, int64_t n_halo, const int6
                       const int64_t *const *ext_offsets, halma_plan **out);
 void halma_plan_destroy(halma_plan *plan);
 
-/* Host float64 arrays of length offsets[n_halo] (the reference keeps particle data in
+/* Host OR device float64 arrays (unified addressing tells them apart) of length offsets[n_halo] (the reference keeps particle data in
  * float64; the float32 cast of positions and masses for the potential is done on the
  * device with round-to-nearest, like np.float32(...) at halo_gas.py:172-178). */
 int halma_plan_upload_members(halma_plan *plan, const double *x, const double *y, const double *z,
@@ -255,14 +255,23 @@ int halma_sigma_projections_f32(int device, int64_t npart, const float *grid, in
  *   were never uploaded contribute nothing.
  * halma_snapshot_upload_particles: kind 0 = DM, 1 = stars; mass already in Msun; id may be
  *   null (the particle index is reported instead).
- * halma_snapshot_gather: gas = one particle at the centre of every cell that is strictly
+ * halma_snapshot_gather: dm_heavy_min = -INFINITY keeps the DM in one group; a finite value splits
+ *   it into the heavy species (mass >= dm_heavy_min, `mandatory` at halo_gas.py:341-345) and the
+ *   light one, each ascending.  counts4 = n_gas, n_dm (all, or heavy), n_dm_light, n_star.
+ *   gas = one particle at the centre of every cell that is strictly
  *   inside the box [c - R, c + R]^3, flagged by cr0amr and solapst, and at distance < R; mass
  *   = (1 + delta) * rho_B * res^3 * mass_scale (mass_scale = rete**3, halo_gas.py:246),
  *   velocity * 3e5; ascending patch, then ix, iy, iz -- bit-identical to the reference's
  *   float64 arrays.  DM / stars = particles with squared distance <= R^2, ASCENDING index (the
- *   reference's KD-tree returns the same set in tree order).  counts3 = n_gas, n_dm, n_star.
+ *   reference's KD-tree returns the same set in tree order).
  * halma_snapshot_fetch: copies the last gather's result to host arrays: gas8 = x, y, z, vx,
- *   vy, vz, mass, temp; dm4 / st4 = x, y, z, mass; st_id = star ids.  Any pointer may be null.
+ *   vy, vz, mass, temp; dm4 / dml4 / st4 = x, y, z, mass; st_id = star ids.  Any pointer may be null.
+ * halma_snapshot_result_device: the same result as DEVICE addresses (ptr4[g] + k * counts4[g] is
+ *   column k of group g = gas, DM, light DM, stars), valid until the next gather or destroy.
+ *   halma_plan_upload_members / _group / _temp accept them directly (they take host or device
+ *   pointers), so a halo can go from the resident snapshot through the unbinding loop without
+ *   touching the host.
+ * halma_snapshot_fetch_star: x, y, z, mass and id of gathered star k (the most bound particle).
  * ------------------------------------------------------------------------------------ */
 /* CUDA-event time (ms) of the kernels of the last halma_halo_shape_f32 /
  * halma_sigma_projections_f32 / halma_snapshot_gather call made on this thread. */
@@ -280,9 +289,11 @@ int halma_snapshot_upload_patch(halma_snapshot *snap, int64_t patch, const float
 int halma_snapshot_upload_particles(halma_snapshot *snap, int kind, int64_t n, const double *x, const double *y,
                                     const double *z, const double *mass, const int64_t *id);
 int halma_snapshot_gather(halma_snapshot *snap, double cx, double cy, double cz, double R, double rho_B,
-                          double mass_scale, int64_t *counts3);
-int halma_snapshot_fetch(halma_snapshot *snap, double *const *gas8, double *const *dm4, double *const *st4,
-                         int64_t *st_id);
+                          double mass_scale, double dm_heavy_min, int64_t *counts4);
+int halma_snapshot_fetch(halma_snapshot *snap, double *const *gas8, double *const *dm4, double *const *dml4,
+                         double *const *st4, int64_t *st_id);
+int halma_snapshot_result_device(halma_snapshot *snap, double **ptr4, int64_t **st_id, int64_t *counts4);
+int halma_snapshot_fetch_star(halma_snapshot *snap, int64_t k, double *xyzm4, int64_t *id);
 
 /* ------------------------------------------------------------------------------------ *
  * Pipe-rate microbenchmark used for the roofline denominator: measures

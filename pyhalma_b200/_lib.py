@@ -26,6 +26,7 @@ EXPORTS = (
     "halma_halo_shape_f32", "halma_sigma_projections_f32",
     "halma_snapshot_create", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_snapshot_upload_patch",
     "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_fetch", "halma_last_kernel_ms",
+    "halma_snapshot_result_device", "halma_snapshot_fetch_star",
 )
 
 
@@ -109,8 +110,10 @@ def lib() -> C.CDLL:
     L.halma_last_kernel_ms.restype = C.c_double
     L.halma_snapshot_upload_patch.argtypes = [vp, i64] + [vp] * 7
     L.halma_snapshot_upload_particles.argtypes = [vp, i32, i64] + [vp] * 5
-    L.halma_snapshot_gather.argtypes = [vp] + [C.c_double] * 6 + [vp]
-    L.halma_snapshot_fetch.argtypes = [vp] * 5
+    L.halma_snapshot_gather.argtypes = [vp] + [C.c_double] * 7 + [vp]
+    L.halma_snapshot_fetch.argtypes = [vp] * 6
+    L.halma_snapshot_result_device.argtypes = [vp] * 4
+    L.halma_snapshot_fetch_star.argtypes = [vp, i64, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("halma_last_error", "halma_potential_workspace_bytes", "halma_plan_destroy",

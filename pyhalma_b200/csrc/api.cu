@@ -915,7 +915,7 @@ extern "C" int halma_plan_upload_members(halma_plan *P, const double *x, const d
     const size_t NU = static_cast<size_t>(P->n_user);
     for (int k = 0; k < 7; ++k) {
         if (NU && !src[k]) return fail(HALMA_ERR_INVALID, "null member array");
-        if (NU) CU_TRY(cudaMemcpyAsync(P->d_in.p + k * NU, src[k], NU * 8, cudaMemcpyHostToDevice, P->stream));
+        if (NU) CU_TRY(cudaMemcpyAsync(P->d_in.p + k * NU, src[k], NU * 8, cudaMemcpyDefault, P->stream));
     }
     P->members_up = true;
     P->sorted_dirty = true;
@@ -934,7 +934,7 @@ extern "C" int halma_plan_upload_group(halma_plan *P, int group, const double *m
         const double *src[4] = {mass, x, y, z};
         // the staging buffer is reused by the next group: stream order keeps this safe
         for (int k = 0; k < 4; ++k)
-            CU_TRY(cudaMemcpyAsync(P->d_stage.p + k * n, src[k], n * 8, cudaMemcpyHostToDevice, P->stream));
+            CU_TRY(cudaMemcpyAsync(P->d_stage.p + k * n, src[k], n * 8, cudaMemcpyDefault, P->stream));
         const size_t NE = static_cast<size_t>(P->n_ext_pad);
         float *e = P->d_ext.p;
         CU_TRY(launch_pack_group(P->d_halo.p, static_cast<int>(P->n_halo), P->group_seg[group], P->group_max[group],
@@ -952,7 +952,7 @@ extern "C" int halma_plan_upload_temp(halma_plan *P, const double *temp, double 
     CU_TRY(cudaSetDevice(P->cfg.device));
     if (P->n_user) {
         if (!temp) return fail(HALMA_ERR_INVALID, "null temperature array");
-        CU_TRY(cudaMemcpyAsync(P->d_temp.p, temp, P->n_user * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+        CU_TRY(cudaMemcpyAsync(P->d_temp.p, temp, P->n_user * sizeof(double), cudaMemcpyDefault, P->stream));
     }
     P->temp_up = true;
     P->cold_T = cold_T;

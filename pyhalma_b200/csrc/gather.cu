@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
@@ -165,6 +166,8 @@ struct BallSel {
     const double *x, *y, *z, *mass;
     const int64_t *id;            // may be null
     Query q;
+    int species;                  // 0 all; 1 heavy: mass >= m_split; 2 light: !(mass >= m_split)   (halo_gas.py:347,362)
+    double m_split;
     double *out[4];
     int64_t *out_id;
 
@@ -177,7 +180,10 @@ struct BallSel {
         // KDTree.query_ball_point: squared distance <= R^2 (halo_gas.py:255,269)
         const double dx = __dsub_rn(x[i], q.cx), dy = __dsub_rn(y[i], q.cy), dz = __dsub_rn(z[i], q.cz);
         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        return d2 <= q.R2;
+        if (!(d2 <= q.R2)) return false;
+        if (species == 0) return true;
+        const bool heavy = mass[i] >= m_split;    // NaN is light, like np.logical_not(condition_l01)
+        return species == 1 ? heavy : !heavy;
     }
     __device__ __forceinline__ void emit(const Item &it, int64_t o) const
     {
@@ -254,8 +260,10 @@ struct halma_snapshot {
     int64_t *d_chunk = nullptr;         // counts then offsets
     size_t chunk_cap = 0;
     // results of the last gather
-    int64_t n_out[3] = {0, 0, 0};
-    double *d_out[3] = {nullptr, nullptr, nullptr};     // gas 8 x n, dm 4 x n, stars 4 x n
+    // gas 8 x n; DM 4 x n (all of it, or the heavy species when a mass split was asked for);
+    // light DM 4 x n; stars 4 x n
+    int64_t n_out[4] = {0, 0, 0, 0};
+    double *d_out[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t *d_out_id = nullptr;
     bool have_result = false;
 };
@@ -288,7 +296,7 @@ int ensure_chunks(halma_snapshot *s, int64_t nchunk)
 
 void free_results(halma_snapshot *s)
 {
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
         if (s->d_out[k]) cudaFreeAsync(s->d_out[k], s->stream);
         s->d_out[k] = nullptr;
         s->n_out[k] = 0;
@@ -454,9 +462,10 @@ extern "C" int halma_snapshot_upload_particles(halma_snapshot *s, int kind, int6
 }
 
 extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, double cz, double R, double rho_B,
-                                     double mass_scale, int64_t *counts3)
+                                     double mass_scale, double dm_heavy_min, int64_t *counts4)
 {
-    if (!s || !counts3) return halma_internal_fail(HALMA_ERR_INVALID, "null pointer");
+    if (!s || !counts4) return halma_internal_fail(HALMA_ERR_INVALID, "null pointer");
+    if (dm_heavy_min != dm_heavy_min) return halma_internal_fail(HALMA_ERR_INVALID, "dm_heavy_min is NaN");
     GA_TRY(cudaSetDevice(s->device));
     free_results(s);
     Query q;
@@ -511,8 +520,12 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
         return HALMA_OK;
     });
     if (rc) return rc;
-    // ---- DM and stars ----
-    for (int kind = 0; kind < 2; ++kind) {
+    // ---- DM (one or two species) and stars ----
+    const double inf = std::numeric_limits<double>::infinity();
+    const bool split = dm_heavy_min > -inf;
+    for (int sel_id = 1; sel_id < 4; ++sel_id) {
+        if (sel_id == 2 && !split) continue;
+        const int kind = sel_id == 3 ? 1 : 0;
         const int64_t n = s->n_part[kind];
         BallSel bs;
         const size_t nn = static_cast<size_t>(std::max<int64_t>(n, 1));
@@ -522,11 +535,13 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
         bs.mass = s->d_part[kind] ? s->d_part[kind] + 3 * nn : nullptr;
         bs.id = s->d_id[kind];
         bs.q = q;
+        bs.species = (split && sel_id != 3) ? sel_id : 0;
+        bs.m_split = dm_heavy_min;
         bs.out_id = nullptr;
-        rc = run_selection(s, bs, n, &s->n_out[1 + kind], [&](BallSel &sel, int64_t total) -> int {
+        rc = run_selection(s, bs, n, &s->n_out[sel_id], [&](BallSel &sel, int64_t total) -> int {
             if (total > 0) {
-                GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_out[1 + kind]), 4 * total * sizeof(double), s->stream));
-                for (int k = 0; k < 4; ++k) sel.out[k] = s->d_out[1 + kind] + k * total;
+                GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_out[sel_id]), 4 * total * sizeof(double), s->stream));
+                for (int k = 0; k < 4; ++k) sel.out[k] = s->d_out[sel_id] + k * total;
                 if (kind == 1) {
                     GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_out_id), total * sizeof(int64_t), s->stream));
                     sel.out_id = s->d_out_id;
@@ -539,28 +554,57 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
     timer.stop();
     GA_TRY(cudaStreamSynchronize(s->stream));
     timer.publish();
-    for (int k = 0; k < 3; ++k) counts3[k] = s->n_out[k];
+    for (int k = 0; k < 4; ++k) counts4[k] = s->n_out[k];
     s->have_result = true;
     return HALMA_OK;
 }
 
-extern "C" int halma_snapshot_fetch(halma_snapshot *s, double *const *gas8, double *const *dm4, double *const *st4,
-                                    int64_t *st_id)
+extern "C" int halma_snapshot_fetch(halma_snapshot *s, double *const *gas8, double *const *dm4, double *const *dml4,
+                                    double *const *st4, int64_t *st_id)
 {
     if (!s) return halma_internal_fail(HALMA_ERR_INVALID, "snapshot is null");
     if (!s->have_result) return halma_internal_fail(HALMA_ERR_STATE, "halma_snapshot_fetch before halma_snapshot_gather");
     GA_TRY(cudaSetDevice(s->device));
-    double *const *dst[3] = {gas8, dm4, st4};
-    const int ncol[3] = {8, 4, 4};
-    for (int g = 0; g < 3; ++g) {
+    double *const *dst[4] = {gas8, dm4, dml4, st4};
+    const int ncol[4] = {8, 4, 4, 4};
+    for (int g = 0; g < 4; ++g) {
         const int64_t n = s->n_out[g];
         if (!dst[g] || n == 0) continue;
         for (int k = 0; k < ncol[g]; ++k)
             if (dst[g][k])
                 GA_TRY(cudaMemcpyAsync(dst[g][k], s->d_out[g] + k * n, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     }
-    if (st_id && s->n_out[2] > 0)
-        GA_TRY(cudaMemcpyAsync(st_id, s->d_out_id, s->n_out[2] * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+    if (st_id && s->n_out[3] > 0)
+        GA_TRY(cudaMemcpyAsync(st_id, s->d_out_id, s->n_out[3] * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+    GA_TRY(cudaStreamSynchronize(s->stream));
+    return HALMA_OK;
+}
+
+// Device addresses of the last gather's result (column k of group g at ptr[g] + k * n_g), valid
+// until the next gather or destroy.  The halma_plan_upload_* entry points take them as they are.
+extern "C" int halma_snapshot_result_device(halma_snapshot *s, double **ptr4, int64_t **st_id, int64_t *counts4)
+{
+    if (!s || !ptr4) return halma_internal_fail(HALMA_ERR_INVALID, "null pointer");
+    if (!s->have_result) return halma_internal_fail(HALMA_ERR_STATE, "no gather result");
+    for (int g = 0; g < 4; ++g) {
+        ptr4[g] = s->d_out[g];
+        if (counts4) counts4[g] = s->n_out[g];
+    }
+    if (st_id) *st_id = s->d_out_id;
+    return HALMA_OK;
+}
+
+// Position, mass and id of gathered star k (the most bound one, halo_gas.py:629-634).
+extern "C" int halma_snapshot_fetch_star(halma_snapshot *s, int64_t k, double *xyzm4, int64_t *id)
+{
+    if (!s || !xyzm4) return halma_internal_fail(HALMA_ERR_INVALID, "null pointer");
+    if (!s->have_result) return halma_internal_fail(HALMA_ERR_STATE, "no gather result");
+    const int64_t n = s->n_out[3];
+    if (k < 0 || k >= n) return halma_internal_fail(HALMA_ERR_INVALID, "star index out of range");
+    GA_TRY(cudaSetDevice(s->device));
+    for (int c = 0; c < 4; ++c)
+        GA_TRY(cudaMemcpyAsync(xyzm4 + c, s->d_out[3] + c * n + k, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (id) GA_TRY(cudaMemcpyAsync(id, s->d_out_id + k, sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
     GA_TRY(cudaStreamSynchronize(s->stream));
     return HALMA_OK;
 }

@@ -93,13 +93,16 @@ class Snapshot:
         _lib.check(self._L.halma_snapshot_upload_particles(self._h, kind, len(x), x.ctypes.data, y.ctypes.data,
                                                            z.ctypes.data, mass.ctypes.data, idp))
 
-    def gather(self, cx, cy, cz, R, rho_B, rete=1.0, *, gas=True, dm=True, stars=True):
-        """Returns the 17-tuple of st_gas_dm_particles_inside (halo_gas.py:276-277); classes that
-        are switched off come back empty."""
-        counts = (C.c_int64 * 3)()
+    def _gather(self, cx, cy, cz, R, rho_B, rete, dm_heavy_min):
+        counts = (C.c_int64 * 4)()
         _lib.check(self._L.halma_snapshot_gather(self._h, float(cx), float(cy), float(cz), float(R), float(rho_B),
-                                                 float(rete) ** 3, counts))
-        ng, nd, ns = (int(c) for c in counts)
+                                                 float(rete) ** 3, float(dm_heavy_min), counts))
+        return tuple(int(c) for c in counts)
+
+    def gather(self, cx, cy, cz, R, rho_B, rete=1.0, *, gas=True, dm=True, stars=True):
+        """Returns the 17-tuple of st_gas_dm_particles_inside (halo_gas.py:276-277) as host arrays;
+        classes that are switched off come back empty."""
+        ng, nd, _, ns = self._gather(cx, cy, cz, R, rho_B, rete, -np.inf)
         g = [np.empty(ng if gas else 0) for _ in range(8)]
         d = [np.empty(nd if dm else 0) for _ in range(4)]
         s = [np.empty(ns if stars else 0) for _ in range(4)]
@@ -108,9 +111,26 @@ class Snapshot:
         def ptrs(arrs, on):
             return (C.c_void_p * len(arrs))(*[a.ctypes.data if on else None for a in arrs])
 
-        _lib.check(self._L.halma_snapshot_fetch(self._h, ptrs(g, gas and ng), ptrs(d, dm and nd), ptrs(s, stars and ns),
-                                                sid.ctypes.data if stars and ns else None))
+        _lib.check(self._L.halma_snapshot_fetch(self._h, ptrs(g, gas and ng), ptrs(d, dm and nd), None,
+                                                ptrs(s, stars and ns), sid.ctypes.data if stars and ns else None))
         return (*g, *d, *s, sid.astype(self.oripa_dtype, copy=False))
+
+    def gather_device(self, cx, cy, cz, R, rho_B, rete=1.0, *, dm_heavy_min=None) -> "DeviceGather":
+        """The same selection left on the GPU.  dm_heavy_min splits the DM into the heavy species
+        (mass >= dm_heavy_min, halo_gas.py:347) and the light one.  The handle is valid until the
+        next gather on this snapshot."""
+        counts = self._gather(cx, cy, cz, R, rho_B, rete, -np.inf if dm_heavy_min is None else dm_heavy_min)
+        ptr = (C.c_void_p * 4)()
+        sid = C.c_void_p()
+        _lib.check(self._L.halma_snapshot_result_device(self._h, ptr, C.byref(sid), None))
+        return DeviceGather(self, counts, [p or 0 for p in ptr], sid.value or 0, dm_heavy_min is not None)
+
+    def fetch_star(self, k: int):
+        """x, y, z, mass, id of gathered star k."""
+        out = np.empty(4)
+        sid = C.c_int64()
+        _lib.check(self._L.halma_snapshot_fetch_star(self._h, int(k), out.ctypes.data, C.byref(sid)))
+        return out[0], out[1], out[2], out[3], np.asarray(sid.value).astype(self.oripa_dtype)[()]
 
     def close(self) -> None:
         if self._h:
@@ -128,6 +148,34 @@ class Snapshot:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class DeviceGather:
+    """Device addresses of one gather: column k of a group is at ptr + 8 * k * n.  Groups: gas
+    (x, y, z, vx, vy, vz, mass, temp), dm (all DM, or the heavy species), dm_light, stars
+    (x, y, z, mass)."""
+
+    def __init__(self, snap, counts, ptrs, st_id_ptr, split):
+        self.snap = snap
+        self.n_gas, self.n_dm, self.n_dm_light, self.n_st = counts
+        self._ptr = ptrs
+        self.st_id_ptr = st_id_ptr
+        self.split = split
+
+    def col(self, group: int, k: int) -> int:
+        n = (self.n_gas, self.n_dm, self.n_dm_light, self.n_st)[group]
+        return self._ptr[group] + 8 * k * n if n else 0
+
+    # (mass, x, y, z) address tuples in the argument order of upload_group
+    def gas_source(self):
+        return self.n_gas, (self.col(0, 6), self.col(0, 0), self.col(0, 1), self.col(0, 2))
+
+    def dm_source(self, light=False):
+        g = 2 if light else 1
+        return (self.n_dm_light if light else self.n_dm), (self.col(g, 3), self.col(g, 0), self.col(g, 1), self.col(g, 2))
+
+    def star_source(self):
+        return self.n_st, (self.col(3, 3), self.col(3, 0), self.col(3, 1), self.col(3, 2))
 
 
 # The reference passes the same snapshot objects for every halo of a snapshot (pyHALMA.py:930-1037);

@@ -182,6 +182,17 @@ class UnbindPlan:
         self._keep.append(arrs)
         _lib.check(self._L.halma_plan_upload_group(self._h, group, *[a.ctypes.data for a in arrs]))
 
+    # Raw addresses (host or device, e.g. gather.DeviceGather columns): no conversion, no copy on the
+    # host.  The caller keeps the memory alive and unchanged until run() returns.
+    def upload_members_raw(self, x, y, z, vx, vy, vz, mass):
+        _lib.check(self._L.halma_plan_upload_members(self._h, *[C.c_void_p(int(a)) for a in (x, y, z, vx, vy, vz, mass)]))
+
+    def upload_group_raw(self, group: int, mass, x, y, z):
+        _lib.check(self._L.halma_plan_upload_group(self._h, group, *[C.c_void_p(int(a)) for a in (mass, x, y, z)]))
+
+    def upload_temp_raw(self, temp, cold_T: float = 5 * 1e4):
+        _lib.check(self._L.halma_plan_upload_temp(self._h, C.c_void_p(int(temp)), float(cold_T)))
+
     def upload_temp(self, temp, cold_T: float = 5 * 1e4):
         """Member temperatures for the cold / hot mass sums of RPS (halo_gas.py:479-492)."""
         t = _f64(temp)

@@ -98,3 +98,42 @@ def test_gather_feeds_rps_like_the_reference_pipeline(snap):
     b = O.RPS(*want[:16], *vb, 10 ** 9, 8e7, 1)
     np.testing.assert_array_equal(np.array(a), np.array(b.as_tuple()))
     gather.release_cached_snapshot()
+
+
+@pytest.mark.parametrize("num_dm_species", [1, 2])
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_device_resident_potential_stage(snap, num_dm_species, mode):
+    """pyHALMA.py:1023-1067 without host arrays: gather, RPS and most_bound_particle read the
+    gathered particles in HBM; only scalars return.  Checked against the oracle's RPS /
+    most_bound_particle on the oracle's gather."""
+    from oracle import oracle as O
+    from pyhalma_b200 import pipeline
+    mass_dm_part = 8e7                       # synth DM particles weigh 1e7: light unless the limit is lowered
+    s2 = synth.amr_snapshot(**SNAP_KW)
+    dm_m = s2.masclet_dm_data[3].copy()
+    dm_m[::3] *= 8.0                         # a heavy species: mass 8e7 >= 0.9 * 8e7 / 8
+    s2.masclet_dm_data[3] = dm_m
+    vb = synth.BULK_V
+    with gather.Snapshot(s2.L, s2.ncoarse, s2.grid_data, s2.gas_data, s2.masclet_dm_data, s2.masclet_st_data) as dev:
+        for R, off in ((0.012, 0.0), (0.03, 0.004)):
+            cx, cy, cz = s2.centre[0] + off, s2.centre[1] - off, s2.centre[2]
+            rps, mb = pipeline.halo_potential_stage(dev, cx, cy, cz, R, s2.rho_B, s2.rete, *vb, mass_dm_part,
+                                                    num_dm_species, mode=mode)
+            w = call(s2, cx, cy, cz, R, fn=OG.st_gas_dm_particles_inside)
+            variant = "f32seq" if mode == "exact" else "f64acc"
+            want_rps = O.RPS(*w[:16], *vb, 10 ** 9, mass_dm_part, num_dm_species, variant=variant).as_tuple()
+            # ordered float64 sums on the device vs numpy's pairwise sums: 1e-13, not bitwise;
+            # fast mode may move a cell whose energy is within 1e-6 of zero across the boundary
+            tol = 1e-13 if mode == "exact" else 2e-3
+            np.testing.assert_allclose(rps, want_rps, rtol=tol)
+            want_mb = O.most_bound_particle(w[0], w[1], w[2], w[6], *w[8:12], *w[12:16], w[16], 10 ** 9, mass_dm_part,
+                                            variant=variant)
+            assert mb[3] == want_mb[3] and (mb[0], mb[1], mb[2]) == tuple(want_mb[:3])
+        # nothing inside: RPS of an empty gas set is all zeros (halo_gas.py:483-490), no star -> None
+        rps, mb = pipeline.halo_potential_stage(dev, 100.0, 100.0, 100.0, 0.01, s2.rho_B, s2.rete, *vb, mass_dm_part,
+                                                num_dm_species, mode=mode)
+        assert rps == (0.0, 0.0, 0.0, 0.0) and mb is None
+        g = dev.gather_device(*s2.centre, 0.02, s2.rho_B, s2.rete, dm_heavy_min=0.9 * mass_dm_part / 8)
+        full = dev.gather(*s2.centre, 0.02, s2.rho_B, s2.rete)
+        assert g.n_dm + g.n_dm_light == len(full[8]) and g.n_dm == int(np.sum(full[11] >= 0.9 * mass_dm_part / 8))
+        assert g.n_gas == len(full[0]) and g.n_st == len(full[12])
