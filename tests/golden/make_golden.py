@@ -260,7 +260,37 @@ def gather_amr():
     np.savez_compressed(os.path.join(HERE, "gather_amr.npz"), **d)
 
 
+STELLAR_AMR = dict(Rmax=0.012, r_members=0.006, factor_v=3.0)
+
+
+def stellar_amr():
+    """halo_properties.escape_velocity_unbinding_fortran (:282-361) END TO END on the synthetic AMR
+    snapshot: the reference's own DM mask (:289-299), its AMR gather (halo_gas.AMRgrid_to_particles with
+    the real numba patch_to_particles, :313-326) and its energy step, around the oracle kernel.
+    Inputs are regenerated from the seed by the tests."""
+    from python_scripts import halo_gas, halo_properties
+    assert halo_gas.AMRgrid_to_particles.__module__ == "python_scripts.halo_gas"
+    snap = synth.amr_snapshot(**GATHER_SNAPSHOT)
+    st = snap.masclet_st_data
+    cx0, cy0, cz0 = snap.centre
+    r = np.sqrt((st[0] - cx0) ** 2 + (st[1] - cy0) ** 2 + (st[2] - cz0) ** 2)
+    part_list = np.nonzero(r < STELLAR_AMR["r_members"])[0]
+    cx, cy, cz, M = halo_properties.center_of_mass(part_list, st[0], st[1], st[2], st[6])
+    vb = halo_properties.CM_velocity(M, part_list, st[3], st[4], st[5], st[6])
+    CALLS.clear()
+    bound = halo_properties.escape_velocity_unbinding_fortran(
+        snap.rete, snap.L, snap.ncoarse, snap.grid_data, snap.gas_data, snap.masclet_dm_data, cx, cy, cz,
+        vb[0], vb[1], vb[2], STELLAR_AMR["Rmax"], part_list, st[0], st[1], st[2], st[3], st[4], st[5], st[6],
+        STELLAR_AMR["factor_v"], snap.rho_B)
+    d = pack_calls()
+    d.update(bound=np.asarray(bound), part_list=part_list, com=np.array([cx, cy, cz]), vb=np.array(vb),
+             Rmax=np.float64(STELLAR_AMR["Rmax"]), factor_v=np.float64(STELLAR_AMR["factor_v"]))
+    np.savez_compressed(os.path.join(HERE, "stellar_amr.npz"), **d)
+    print("stellar_amr members", len(part_list), "bound", int(np.sum(bound)), "sources", int(d["call0_ntotal"]))
+
+
 if __name__ == "__main__":
     main()
     shape_and_sigma()
     gather_amr()
+    stellar_amr()

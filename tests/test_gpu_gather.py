@@ -137,3 +137,17 @@ def test_device_resident_potential_stage(snap, num_dm_species, mode):
         full = dev.gather(*s2.centre, 0.02, s2.rho_B, s2.rete)
         assert g.n_dm + g.n_dm_light == len(full[8]) and g.n_dm == int(np.sum(full[11] >= 0.9 * mass_dm_part / 8))
         assert g.n_gas == len(full[0]) and g.n_st == len(full[12])
+
+
+def test_stellar_unbinding_end_to_end_golden(snap, golden_dir):
+    """halo_properties.escape_velocity_unbinding_fortran with the reference's signature: AMR gather
+    on the GPU + EXACT kernel reproduce the mask the reference computed end to end."""
+    from pyhalma_b200 import halo_properties
+    from test_oracle_gather import stellar_amr_inputs
+    g = dict(np.load(os.path.join(golden_dir, "stellar_amr.npz")))
+    a = stellar_amr_inputs(snap, g)
+    bound = halo_properties.escape_velocity_unbinding_fortran(*a, mode="exact")
+    np.testing.assert_array_equal(bound.astype(bool), g["bound"])
+    fast = halo_properties.escape_velocity_unbinding_fortran(*a, mode="fast").astype(bool)
+    assert np.count_nonzero(fast != g["bound"]) <= 2          # only energies within 1e-6 of zero may flip
+    gather.release_cached_snapshot()

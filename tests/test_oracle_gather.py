@@ -78,3 +78,31 @@ def test_helpers():
     w = OG.which_patches_inside_box([0, 1, 0, 1, 0, 1], [4, 4, 4], [4, 4, 4], [4, 4, 4], [0., .5, 30.], [0., .5, 30.],
                                     [0., .5, 30.], [0, 2], 40.0, 128)
     assert w == [0, 1]
+
+
+def stellar_amr_inputs(snap, g):
+    st = snap.masclet_st_data
+    return (snap.rete, snap.L, snap.ncoarse, snap.grid_data, snap.gas_data, snap.masclet_dm_data, *g["com"], *g["vb"],
+            float(g["Rmax"]), g["part_list"], st[0], st[1], st[2], st[3], st[4], st[5], st[6], float(g["factor_v"]),
+            snap.rho_B)
+
+
+def test_stellar_unbinding_end_to_end_matches_reference(snap, golden_dir):
+    """escape_velocity_unbinding_fortran run by the reference itself on the AMR snapshot (its own DM
+    mask, AMR gather and energy step) against the oracle's gather + kernel + energy step."""
+    from oracle import oracle as O
+    g = dict(np.load(os.path.join(golden_dir, "stellar_amr.npz")))
+    a = stellar_amr_inputs(snap, g)
+    rete, L, ncoarse, grid_data, gas_data, dm_data, cx, cy, cz, vx, vy, vz, Rmax, part_list = a[:14]
+    st = a[14:21]
+    gx, gy, gz, _, _, _, gm, _ = OG.AMRgrid_to_particles(L, ncoarse, grid_data, gas_data, Rmax, cx, cy, cz, a[22])
+    inside = OG.parallel_inside(gx, gy, gz, Rmax, cx, cy, cz)
+    gas = (gx[inside], gy[inside], gz[inside], gm[inside] * rete ** 3)
+    dins = np.sqrt((dm_data[0] - cx) ** 2 + (dm_data[1] - cy) ** 2 + (dm_data[2] - cz) ** 2) < Rmax
+    dm = tuple(np.asarray(c)[dins] for c in dm_data[:4])
+    stars = tuple(np.asarray(c)[part_list] for c in st)
+    bound, be32, _ = O.escape_velocity_unbinding(gas, stars, dm, (vx, vy, vz), a[21])
+    assert int(g["n_calls"]) == 1 and int(g["call0_ntotal"]) == len(gas[0]) + len(part_list) + len(dm[0])
+    np.testing.assert_array_equal(be32, g["call0_be"])
+    np.testing.assert_array_equal(bound, g["bound"])
+    assert 0 < bound.sum() < len(bound)
