@@ -18,10 +18,12 @@
 //   particles  24 B per particle (twice) + 32..40 B read and written per selected particle
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/halma_unbind.h"
@@ -195,6 +197,142 @@ struct BallSel {
     }
 };
 
+// ---- uniform-grid index over the resident particles ---------------------------------------------
+// The brute-force ball query reads every resident particle for every halo.  Above
+// kIndexMinParticles the particles get a cell list instead: G^3 cells over their bounding box,
+// `perm` = particle indices sorted by cell (x fastest; stable, so ascending inside a cell) and
+// `cell_start`.  The cells a query box overlaps are, per (iy, iz) row, ONE contiguous range of
+// `perm`; only those candidates are tested, with the same predicate as BallSel, and the selected
+// indices are sorted so the output is the brute-force path's (ascending index), bit for bit.
+struct GridGeom {
+    double lo[3], inv_h[3];       // cell = clamp(floor((x - lo) * inv_h), 0, G - 1)
+    int32_t G;
+};
+
+__device__ __forceinline__ int grid_cell(const GridGeom &g, int a, double v)
+{
+    const double f = floor(__dmul_rn(__dsub_rn(v, g.lo[a]), g.inv_h[a]));
+    return static_cast<int>(fmin(fmax(f, 0.0), static_cast<double>(g.G - 1)));      // NaN -> 0
+}
+
+__global__ void __launch_bounds__(256) k_minmax(const double *__restrict__ x, const double *__restrict__ y,
+                                               const double *__restrict__ z, int64_t n, double *__restrict__ part6)
+{
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double v[6] = {inf, inf, inf, -inf, -inf, -inf};
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const double p[3] = {x[i], y[i], z[i]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            v[a] = fmin(v[a], p[a]);
+            v[3 + a] = fmax(v[3 + a], p[a]);
+        }
+    }
+    __shared__ double red[6][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double t = v[k];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_down_sync(0xffffffffu, t, o);
+            t = k < 3 ? fmin(t, u) : fmax(t, u);
+        }
+        if (lane == 0) red[k][warp] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double t = red[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) t = threadIdx.x < 3 ? fmin(t, red[threadIdx.x][w]) : fmax(t, red[threadIdx.x][w]);
+        part6[blockIdx.x * 6 + threadIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cell_keys(const double *__restrict__ x, const double *__restrict__ y,
+                                                  const double *__restrict__ z, int64_t n, const GridGeom g,
+                                                  uint32_t *__restrict__ key, int32_t *__restrict__ idx)
+{
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int ix = grid_cell(g, 0, x[i]), iy = grid_cell(g, 1, y[i]), iz = grid_cell(g, 2, z[i]);
+        key[i] = static_cast<uint32_t>((iz * g.G + iy) * g.G + ix);
+        idx[i] = static_cast<int32_t>(i);
+    }
+}
+
+// cell_start[c] = first position of the sorted keys with key >= c, for c = 0 .. G^3
+__global__ void __launch_bounds__(256) k_cell_start(const uint32_t *__restrict__ sorted_key, int64_t n, int64_t n_cells,
+                                                   int32_t *__restrict__ cell_start)
+{
+    for (int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; c <= n_cells;
+         c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (sorted_key[mid] < c)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        cell_start[c] = static_cast<int32_t>(lo);
+    }
+}
+
+struct RowRange {
+    int32_t ix0, ix1, iy0, ny, iz0, nz, G;
+};
+
+// candidates of every (iy, iz) row of the query's cell box
+__global__ void __launch_bounds__(256) k_row_len(const int32_t *__restrict__ cell_start, const RowRange r,
+                                                int64_t *__restrict__ len)
+{
+    const int rows = r.ny * r.nz;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= rows; t += gridDim.x * blockDim.x) {
+        int64_t v = 0;
+        if (t < rows) {
+            const int iy = r.iy0 + t % r.ny, iz = r.iz0 + t / r.ny;
+            const int64_t base = (static_cast<int64_t>(iz) * r.G + iy) * r.G;
+            v = cell_start[base + r.ix1 + 1] - cell_start[base + r.ix0];
+        }
+        len[t] = v;
+    }
+}
+
+struct IndexedBallSel {
+    BallSel b;
+    const int32_t *perm, *cell_start;
+    const int64_t *row_off;       // exclusive scan of the row lengths, [rows + 1]
+    RowRange r;
+    int32_t *out_idx;
+
+    typedef BallSel::Item Item;
+    __device__ __forceinline__ bool test(int64_t t, Item &it) const
+    {
+        int lo = 0, hi = r.ny * r.nz;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (row_off[mid] <= t)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int iy = r.iy0 + lo % r.ny, iz = r.iz0 + lo / r.ny;
+        const int64_t base = (static_cast<int64_t>(iz) * r.G + iy) * r.G;
+        return b.test(perm[cell_start[base + r.ix0] + (t - row_off[lo])], it);
+    }
+    __device__ __forceinline__ void emit(const Item &it, int64_t o) const { out_idx[o] = static_cast<int32_t>(it.i); }
+};
+
+__global__ void __launch_bounds__(256) k_emit_rows(const BallSel b, const int32_t *__restrict__ idx, int64_t k)
+{
+    for (int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; o < k;
+         o += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        BallSel::Item it;
+        it.i = idx[o];
+        b.emit(it, o);
+    }
+}
+
 template <class Sel>
 __global__ void __launch_bounds__(kSelBlock) k_sel_count(const Sel sel, int64_t n, int64_t *__restrict__ chunk_cnt)
 {
@@ -254,6 +392,11 @@ struct halma_snapshot {
     int64_t n_part[2] = {0, 0};
     double *d_part[2] = {nullptr, nullptr};     // 4 x n
     int64_t *d_id[2] = {nullptr, nullptr};
+    // uniform-grid index per particle kind (built above kIndexMinParticles)
+    bool indexed[2] = {false, false};
+    GridGeom geom[2];
+    int32_t *d_perm[2] = {nullptr, nullptr};
+    int32_t *d_cell_start[2] = {nullptr, nullptr};
     // scratch
     void *d_scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
@@ -334,6 +477,174 @@ int run_selection(halma_snapshot *s, Sel &sel, int64_t n, int64_t *total, Alloc 
     return HALMA_OK;
 }
 
+constexpr int64_t kIndexMinParticles = 1 << 18;      // below this the brute-force pass is a few microseconds
+
+int64_t index_min_particles()
+{
+    const char *e = getenv("HALMA_GATHER_INDEX_MIN");      // tests force the index on small inputs; -1 disables it
+    return e ? static_cast<int64_t>(atoll(e)) : kIndexMinParticles;
+}
+
+int free_index(halma_snapshot *s, int kind)
+{
+    if (s->d_perm[kind]) GA_TRY(cudaFreeAsync(s->d_perm[kind], s->stream));
+    if (s->d_cell_start[kind]) GA_TRY(cudaFreeAsync(s->d_cell_start[kind], s->stream));
+    s->d_perm[kind] = nullptr;
+    s->d_cell_start[kind] = nullptr;
+    s->indexed[kind] = false;
+    return HALMA_OK;
+}
+
+// Cell list of the particles of `kind` (positions already on the device).
+int build_index(halma_snapshot *s, int kind)
+{
+    const int64_t n = s->n_part[kind];
+    const int64_t min_n = index_min_particles();
+    if (min_n < 0 || n < std::max<int64_t>(min_n, 1) || n >= INT32_MAX) return HALMA_OK;
+    const size_t nn = static_cast<size_t>(n);
+    const double *x = s->d_part[kind], *y = x + nn, *z = x + 2 * nn;
+    // bounding box
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(s->sm) * 8));
+    double *d_mm = nullptr;
+    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_mm), blocks * 6 * sizeof(double), s->stream));
+    k_minmax<<<blocks, 256, 0, s->stream>>>(x, y, z, n, d_mm);
+    GA_TRY(cudaGetLastError());
+    std::vector<double> mm(static_cast<size_t>(blocks) * 6);
+    GA_TRY(cudaMemcpyAsync(mm.data(), d_mm, mm.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    GA_TRY(cudaFreeAsync(d_mm, s->stream));
+    GA_TRY(cudaStreamSynchronize(s->stream));
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = mm[a];
+        hi[a] = mm[3 + a];
+        for (int b = 1; b < blocks; ++b) {
+            lo[a] = std::fmin(lo[a], mm[static_cast<size_t>(b) * 6 + a]);
+            hi[a] = std::fmax(hi[a], mm[static_cast<size_t>(b) * 6 + 3 + a]);
+        }
+        if (!std::isfinite(lo[a]) || !std::isfinite(hi[a])) return HALMA_OK;      // infinite extent: keep brute force
+    }
+    GridGeom g;
+    int G = static_cast<int>(std::lround(std::cbrt(static_cast<double>(n) / 4.0)));
+    g.G = std::min(256, std::max(1, G));
+    for (int a = 0; a < 3; ++a) {
+        g.lo[a] = lo[a];
+        const double ext = hi[a] - lo[a];
+        g.inv_h[a] = ext > 0 && std::isfinite(g.G / ext) ? g.G / ext : 0.0;
+    }
+    const int64_t n_cells = static_cast<int64_t>(g.G) * g.G * g.G;
+    uint32_t *d_key = nullptr, *d_key2 = nullptr;
+    int32_t *d_idx = nullptr;
+    void *d_tmp = nullptr;
+    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_key), nn * sizeof(uint32_t), s->stream));
+    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_key2), nn * sizeof(uint32_t), s->stream));
+    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_idx), nn * sizeof(int32_t), s->stream));
+    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_perm[kind]), nn * sizeof(int32_t), s->stream));
+    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_cell_start[kind]), (n_cells + 1) * sizeof(int32_t), s->stream));
+    k_cell_keys<<<blocks, 256, 0, s->stream>>>(x, y, z, n, g, d_key, d_idx);
+    GA_TRY(cudaGetLastError());
+    int bits = 1;
+    while ((int64_t(1) << bits) < n_cells) ++bits;
+    size_t tmp_bytes = 0;
+    GA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_idx, s->d_perm[kind], static_cast<int>(n), 0,
+                                           bits, s->stream));
+    GA_TRY(cudaMallocAsync(&d_tmp, tmp_bytes, s->stream));
+    GA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_idx, s->d_perm[kind], static_cast<int>(n), 0,
+                                           bits, s->stream));
+    const int cb = static_cast<int>(std::min<int64_t>((n_cells + 256) / 256, static_cast<int64_t>(s->sm) * 16));
+    k_cell_start<<<cb, 256, 0, s->stream>>>(d_key2, n, n_cells, s->d_cell_start[kind]);
+    GA_TRY(cudaGetLastError());
+    GA_TRY(cudaFreeAsync(d_tmp, s->stream));
+    GA_TRY(cudaFreeAsync(d_key, s->stream));
+    GA_TRY(cudaFreeAsync(d_key2, s->stream));
+    GA_TRY(cudaFreeAsync(d_idx, s->stream));
+    GA_TRY(cudaStreamSynchronize(s->stream));
+    s->geom[kind] = g;
+    s->indexed[kind] = true;
+    return HALMA_OK;
+}
+
+int host_cell(const GridGeom &g, int a, double v)
+{
+    const double f = std::floor((v - g.lo[a]) * g.inv_h[a]);
+    return static_cast<int>(std::fmin(std::fmax(f, 0.0), static_cast<double>(g.G - 1)));
+}
+
+// Ball selection through the cell list: candidates -> selected indices -> sorted -> rows.
+template <class Alloc>
+int run_indexed_ball(halma_snapshot *s, int kind, BallSel &bs, int64_t *total, Alloc alloc_outputs)
+{
+    *total = 0;
+    const GridGeom &g = s->geom[kind];
+    const Query &q = bs.q;
+    if (!(q.R >= 0)) return alloc_outputs(bs, 0);          // negative or NaN radius selects nothing
+    RowRange r;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        // one cell of slack: the exact test below decides
+        lo[a] = std::max(0, host_cell(g, a, q.box[2 * a]) - 1);
+        hi[a] = std::min(g.G - 1, host_cell(g, a, q.box[2 * a + 1]) + 1);
+    }
+    r.ix0 = lo[0]; r.ix1 = hi[0];
+    r.iy0 = lo[1]; r.ny = hi[1] - lo[1] + 1;
+    r.iz0 = lo[2]; r.nz = hi[2] - lo[2] + 1;
+    r.G = g.G;
+    const int64_t rows = static_cast<int64_t>(r.ny) * r.nz;
+    int64_t *d_len = nullptr;
+    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_len), 2 * (rows + 1) * sizeof(int64_t), s->stream));
+    int64_t *d_off = d_len + rows + 1;
+    k_row_len<<<static_cast<int>((rows + 256) / 256), 256, 0, s->stream>>>(s->d_cell_start[kind], r, d_len);
+    GA_TRY(cudaGetLastError());
+    if (int rc = ensure_scan_tmp(s, rows + 1)) return rc;
+    size_t tmp = s->scan_tmp_bytes;
+    GA_TRY(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, tmp, d_len, d_off, static_cast<int>(rows + 1), s->stream));
+    int64_t n_cand = 0;
+    GA_TRY(cudaMemcpyAsync(&n_cand, d_off + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+    GA_TRY(cudaStreamSynchronize(s->stream));
+    // a query that covers a large part of the particles is cheaper as one streaming pass
+    if (n_cand * 3 > s->n_part[kind]) {
+        GA_TRY(cudaFreeAsync(d_len, s->stream));
+        return run_selection(s, bs, s->n_part[kind], total, alloc_outputs);
+    }
+    IndexedBallSel is;
+    is.b = bs;
+    is.perm = s->d_perm[kind];
+    is.cell_start = s->d_cell_start[kind];
+    is.row_off = d_off;
+    is.r = r;
+    is.out_idx = nullptr;
+    int32_t *d_sel = nullptr, *d_sorted = nullptr;
+    int rc = run_selection(s, is, n_cand, total, [&](IndexedBallSel &sel, int64_t k) -> int {
+        if (k > 0) {
+            GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_sel), 2 * k * sizeof(int32_t), s->stream));
+            d_sorted = d_sel + k;
+            sel.out_idx = d_sel;
+        }
+        return HALMA_OK;
+    });
+    if (rc) return rc;
+    const int64_t k = *total;
+    if (int rc2 = alloc_outputs(bs, k)) return rc2;
+    if (k > 0) {
+        if (k >= INT32_MAX) return halma_internal_fail(HALMA_ERR_TOO_LARGE, "selection too large");
+        void *d_tmp = nullptr;
+        size_t tb = 0;
+        int bits = 1;
+        while ((int64_t(1) << bits) < s->n_part[kind]) ++bits;
+        const uint32_t *kin = reinterpret_cast<const uint32_t *>(d_sel);
+        uint32_t *kout = reinterpret_cast<uint32_t *>(d_sorted);
+        GA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb, kin, kout, static_cast<int>(k), 0, bits, s->stream));
+        GA_TRY(cudaMallocAsync(&d_tmp, tb, s->stream));
+        GA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, tb, kin, kout, static_cast<int>(k), 0, bits, s->stream));
+        const int eb = static_cast<int>(std::min<int64_t>((k + 255) / 256, static_cast<int64_t>(s->sm) * 16));
+        k_emit_rows<<<eb, 256, 0, s->stream>>>(bs, d_sorted, k);
+        GA_TRY(cudaGetLastError());
+        GA_TRY(cudaFreeAsync(d_tmp, s->stream));
+        GA_TRY(cudaFreeAsync(d_sel, s->stream));
+    }
+    GA_TRY(cudaFreeAsync(d_len, s->stream));
+    return HALMA_OK;
+}
+
 }  // namespace
 
 extern "C" int halma_snapshot_create(int device, double L, int32_t ncoarse, int64_t n_patch, const int32_t *level,
@@ -398,7 +709,8 @@ extern "C" void halma_snapshot_destroy(halma_snapshot *s)
     cudaSetDevice(s->device);
     free_results(s);
     void *ptrs[] = {s->d_pd, s->d_sub, s->d_cand, s->d_fields, s->d_flags, s->d_part[0], s->d_part[1],
-                    s->d_id[0], s->d_id[1], s->d_scan_tmp, s->d_chunk};
+                    s->d_id[0], s->d_id[1], s->d_scan_tmp, s->d_chunk, s->d_perm[0], s->d_perm[1],
+                    s->d_cell_start[0], s->d_cell_start[1]};
     for (void *p : ptrs)
         if (p) cudaFreeAsync(p, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -445,6 +757,7 @@ extern "C" int halma_snapshot_upload_particles(halma_snapshot *s, int kind, int6
     s->d_part[kind] = nullptr;
     s->d_id[kind] = nullptr;
     s->n_part[kind] = 0;
+    if (int rc = free_index(s, kind)) return rc;
     if (n) {
         const size_t nn = static_cast<size_t>(n);
         GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_part[kind]), 4 * nn * sizeof(double), s->stream));
@@ -458,7 +771,7 @@ extern "C" int halma_snapshot_upload_particles(halma_snapshot *s, int kind, int6
         GA_TRY(cudaStreamSynchronize(s->stream));
     }
     s->n_part[kind] = n;
-    return HALMA_OK;
+    return build_index(s, kind);
 }
 
 extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, double cz, double R, double rho_B,
@@ -538,7 +851,7 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
         bs.species = (split && sel_id != 3) ? sel_id : 0;
         bs.m_split = dm_heavy_min;
         bs.out_id = nullptr;
-        rc = run_selection(s, bs, n, &s->n_out[sel_id], [&](BallSel &sel, int64_t total) -> int {
+        auto alloc = [&](BallSel &sel, int64_t total) -> int {
             if (total > 0) {
                 GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_out[sel_id]), 4 * total * sizeof(double), s->stream));
                 for (int k = 0; k < 4; ++k) sel.out[k] = s->d_out[sel_id] + k * total;
@@ -548,7 +861,9 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
                 }
             }
             return HALMA_OK;
-        });
+        };
+        rc = s->indexed[kind] ? run_indexed_ball(s, kind, bs, &s->n_out[sel_id], alloc)
+                              : run_selection(s, bs, n, &s->n_out[sel_id], alloc);
         if (rc) return rc;
     }
     timer.stop();

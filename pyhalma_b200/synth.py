@@ -356,11 +356,12 @@ class AmrSnapshot:
 
 def amr_snapshot(n_levels: int = 5, patches_per_level: int = 3, n_dm: int = 20_000, n_st: int = 30_000,
                  seed_extra: int = 0, L: float = 40.0, ncoarse: int = 128, centre=CENTRE,
-                 max_cells: int = 28, base_cells: int = 4) -> AmrSnapshot:
+                 max_cells: int = 28, base_cells: int = 4, background_frac: float = 0.0) -> AmrSnapshot:
     """Nested patches around `centre`: level l has `patches_per_level` patches of up to
     max_cells^3 cells of size (L/ncoarse)/2^l, aligned to the parent grid, partly overlapping;
     cr0amr marks cells covered by a finer patch, solapst cells already covered by an earlier
-    patch of the same level; a few flags are flipped at random."""
+    patch of the same level; a few flags are flipped at random.  background_frac of the DM and
+    star particles is spread uniformly over the whole box (a cosmological volume around the halo)."""
     rng = rng_for(6, seed_extra)
     c = np.asarray(centre, dtype=np.float64)
     npatch = [0]
@@ -419,6 +420,11 @@ def amr_snapshot(n_levels: int = 5, patches_per_level: int = 3, n_dm: int = 20_0
     gas_data = [delta, vx, vy, vz, temp, cr0, sol]
     dm = dm_cloud(n_dm, 60 * KPC, 8e7 / 8, rng, centre=centre)
     st = plummer_stars(n_st, 8 * KPC, 1e6, rng, centre=centre)
+    if background_frac > 0:
+        for p_, n_ in ((dm, n_dm), (st, n_st)):
+            k = int(background_frac * n_)
+            which = rng.choice(n_, k, replace=False)
+            p_.x[which], p_.y[which], p_.z[which] = (rng.uniform(-L / 2, L / 2, k) for _ in range(3))
     dm_data = [dm.x, dm.y, dm.z, dm.mass]
     st_data = [st.x, st.y, st.z, st.vx, st.vy, st.vz, st.mass, None, None, np.arange(n_st, dtype=np.int64) + 7_000_000]
     return AmrSnapshot(L, ncoarse, grid_data, gas_data, dm_data, st_data, rho_B=3.9e10, rete=0.8, centre=tuple(c))

@@ -151,3 +151,48 @@ def test_stellar_unbinding_end_to_end_golden(snap, golden_dir):
     fast = halo_properties.escape_velocity_unbinding_fortran(*a, mode="fast").astype(bool)
     assert np.count_nonzero(fast != g["bound"]) <= 2          # only energies within 1e-6 of zero may flip
     gather.release_cached_snapshot()
+
+
+def test_grid_index_equals_brute_force(snap, monkeypatch):
+    """Above 2^18 resident particles the ball query goes through a cell list; the result must be the
+    brute-force pass's, bit for bit and in the same order.  Forced on here with the small snapshot,
+    plus one case at the real threshold."""
+    rng = np.random.default_rng(8)
+    queries = [(np.asarray(snap.centre) + rng.normal(0, 0.02, 3), float(10 ** rng.uniform(-3.5, -0.5)))
+               for _ in range(25)]
+    queries += [(np.asarray(snap.centre), 0.0), (np.asarray(snap.centre), 1e3), (np.asarray(snap.centre) + 50.0, 0.01)]
+
+    def run(min_particles, s_):
+        monkeypatch.setenv("HALMA_GATHER_INDEX_MIN", str(min_particles))
+        with gather.Snapshot(s_.L, s_.ncoarse, s_.grid_data, s_.gas_data, s_.masclet_dm_data, s_.masclet_st_data) as dev:
+            out = [dev.gather(*c, R, s_.rho_B, s_.rete) for c, R in queries]
+            g = dev.gather_device(*queries[0][0], 0.03, s_.rho_B, s_.rete, dm_heavy_min=1e7)
+            out.append((g.n_dm, g.n_dm_light, g.n_st))
+        return out
+
+    brute, indexed = run(-1, snap), run(1, snap)
+    assert any(len(o[8]) > 100 for o in brute[:-1]) and any(len(o[12]) > 1000 for o in brute[:-1])
+    for a, b in zip(brute[:-1], indexed[:-1]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    assert brute[-1] == indexed[-1]
+    # coincident particles, a particle with NaN position and one far outlier must not break the grid
+    s2 = synth.amr_snapshot(**SNAP_KW)
+    dm = [np.array(a, dtype=np.float64) for a in s2.masclet_dm_data]
+    dm[0][:50] = dm[0][50]; dm[1][:50] = dm[1][50]; dm[2][:50] = dm[2][50]
+    dm[0][100] = np.nan
+    dm[1][101] = 1e6
+    s2.masclet_dm_data = dm
+    b2, i2 = run(-1, s2), run(1, s2)
+    for a, b in zip(b2[:-1], i2[:-1]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    monkeypatch.delenv("HALMA_GATHER_INDEX_MIN")
+    big = synth.amr_snapshot(n_levels=3, n_dm=400_000, n_st=300_000)         # default threshold: indexed
+    with gather.Snapshot(big.L, big.ncoarse, big.grid_data, big.gas_data, big.masclet_dm_data, big.masclet_st_data) as dev:
+        got = dev.gather(*big.centre, 0.02, big.rho_B, big.rete)
+    want = OG.st_gas_dm_particles_inside(big.rete, big.L, big.ncoarse, big.grid_data, big.gas_data, big.masclet_dm_data,
+                                         big.masclet_st_data, None, None, *big.centre, 0.02, big.rho_B)
+    assert len(got[8]) > 1000 and len(got[12]) > 1000
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
