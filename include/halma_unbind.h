@@ -295,6 +295,13 @@ int halma_snapshot_fetch(halma_snapshot *snap, double *const *gas8, double *cons
 int halma_snapshot_result_device(halma_snapshot *snap, double **ptr4, int64_t **st_id, int64_t *counts4);
 int halma_snapshot_fetch_star(halma_snapshot *snap, int64_t k, double *xyzm4, int64_t *id);
 
+/* EXACT mode computes rn(m / rn(sqrt(r^2))) with branch-free sequences while the operands are
+ * in a safe exponent window and with the IEEE library routines otherwise.  This self-test
+ * compares the two on the device: all 2^24 (mantissa, exponent parity) inputs of the square
+ * root plus n_random pseudo-random (m, r^2) pairs over the whole window; *mismatches must
+ * come back 0. */
+int halma_selftest_exact_arith(int device, int64_t n_random, uint64_t seed, int64_t *mismatches);
+
 /* ------------------------------------------------------------------------------------ *
  * Pipe-rate microbenchmark used for the roofline denominator: measures
  * MUFU.RSQ, FFMA and packed FFMA2 issue rates per SM per clock, and the SM clock during

@@ -112,6 +112,22 @@ static thread_local double g_last_kernel_ms = 0.0;
 void halma_internal_set_kernel_ms(double ms) { g_last_kernel_ms = ms; }
 extern "C" double halma_last_kernel_ms(void) { return g_last_kernel_ms; }
 
+extern "C" int halma_selftest_exact_arith(int device, int64_t n_random, uint64_t seed, int64_t *mismatches)
+{
+    if (!mismatches || n_random < 0) return fail(HALMA_ERR_INVALID, "bad argument");
+    DeviceCtx *c;
+    if (int rc = get_ctx(device, &c)) return rc;
+    unsigned long long *d = nullptr, h = 0;
+    CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d), sizeof h, c->stream));
+    CU_TRY(cudaMemsetAsync(d, 0, sizeof h, c->stream));
+    CU_TRY(potential_selftest_exact(n_random, seed, d, c->sm_count, c->stream));
+    CU_TRY(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaFreeAsync(d, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *mismatches = static_cast<int64_t>(h);
+    return HALMA_OK;
+}
+
 extern "C" int halma_device_count(int *count)
 {
     if (!count) return fail(HALMA_ERR_INVALID, "count is null");

@@ -514,6 +514,22 @@ __device__ __forceinline__ float term_exact(float xs, float ys, float zs, float 
     return take ? q : 0.f;
 }
 
+// The same term through exact_term_fast (halma_common.cuh): bit-identical while the operands are
+// in the safe window, which `bad` reports for pairs that pass the predicate.  The predicate stays
+// the literal != on the inputs (a three-input min of |d| would differ for NaN and Inf coordinates).
+__device__ __forceinline__ float term_exact_fast(float xs, float ys, float zs, float m, float xi, float yi, float zi,
+                                                 bool &bad)
+{
+    const float dx = __fsub_rn(xs, xi);
+    const float dy = __fsub_rn(ys, yi);
+    const float dz = __fsub_rn(zs, zi);
+    const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const bool take = (xs != xi) && (ys != yi) && (zs != zi);
+    bad |= take && !exact_r2_safe(r2);
+    const float q = exact_term_fast(m, r2);
+    return take ? q : 0.f;
+}
+
 __device__ __forceinline__ void tile_exact(const float *__restrict__ stage, int len, float xi, float yi, float zi,
                                            float &acc)
 {
@@ -522,18 +538,87 @@ __device__ __forceinline__ void tile_exact(const float *__restrict__ stage, int 
     const float4 *Z = reinterpret_cast<const float4 *>(stage + 2 * kTileJ);
     const float4 *M = reinterpret_cast<const float4 *>(stage + 3 * kTileJ);
     const int nq = (len + 3) >> 2;
+    // masses are per source: every lane vets four of the tile's 128 once, instead of every
+    // lane vetting every source
+    const int lane = threadIdx.x & 31;
+    const float4 mq = M[lane];
+    const bool m_ok = lane >= nq || (exact_mass_safe(mq.x) && exact_mass_safe(mq.y) && exact_mass_safe(mq.z) &&
+                                     exact_mass_safe(mq.w));
+    const bool fast_ok = __all_sync(0xffffffffu, m_ok);
 #pragma unroll 2
     for (int q = 0; q < nq; ++q) {
         const float4 x4 = X[q], y4 = Y[q], z4 = Z[q], m4 = M[q];
-        const float t0 = term_exact(x4.x, y4.x, z4.x, m4.x, xi, yi, zi);
-        const float t1 = term_exact(x4.y, y4.y, z4.y, m4.y, xi, yi, zi);
-        const float t2 = term_exact(x4.z, y4.z, z4.z, m4.z, xi, yi, zi);
-        const float t3 = term_exact(x4.w, y4.w, z4.w, m4.w, xi, yi, zi);
+        float t0, t1, t2, t3;
+        bool bad = !fast_ok;
+        if (fast_ok) {
+            t0 = term_exact_fast(x4.x, y4.x, z4.x, m4.x, xi, yi, zi, bad);
+            t1 = term_exact_fast(x4.y, y4.y, z4.y, m4.y, xi, yi, zi, bad);
+            t2 = term_exact_fast(x4.z, y4.z, z4.z, m4.z, xi, yi, zi, bad);
+            t3 = term_exact_fast(x4.w, y4.w, z4.w, m4.w, xi, yi, zi, bad);
+        }
+        if (__any_sync(0xffffffffu, bad)) {          // an operand outside the window: IEEE library path
+            t0 = term_exact(x4.x, y4.x, z4.x, m4.x, xi, yi, zi);
+            t1 = term_exact(x4.y, y4.y, z4.y, m4.y, xi, yi, zi);
+            t2 = term_exact(x4.z, y4.z, z4.z, m4.z, xi, yi, zi);
+            t3 = term_exact(x4.w, y4.w, z4.w, m4.w, xi, yi, zi);
+        }
         acc = __fadd_rn(acc, t0);      // ascending source order, one rounding per add
         acc = __fadd_rn(acc, t1);
         acc = __fadd_rn(acc, t2);
         acc = __fadd_rn(acc, t3);
     }
+}
+
+// Device self-test of exact_term_fast against __fdiv_rn(m, __fsqrt_rn(r2)).
+// part 0: every float32 mantissa x both exponent parities of r2 (the square root only depends on
+//         those), m = 1;  part 1: pseudo-random (m, r2) over the whole safe window.
+__global__ void k_selftest_exact(int64_t n_random, uint64_t seed, unsigned long long *mismatch)
+{
+    const int64_t n_sqrt = int64_t(1) << 24;
+    const int64_t total = n_sqrt + n_random;
+    unsigned long long bad = 0;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float m, r2;
+        if (i < n_sqrt) {
+            const uint32_t mant = static_cast<uint32_t>(i) & 0x7fffffu, par = static_cast<uint32_t>(i >> 23);
+            r2 = __uint_as_float(((110u + par) << 23) | mant);
+            m = 1.0f;
+        } else {
+            uint64_t z = seed + 0x9e3779b97f4a7c15ull * static_cast<uint64_t>(i);       // splitmix64
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            z ^= z >> 31;
+            uint64_t w = (z ^ 0xd1b54a32d192ed03ull) * 0x2545f4914f6cdd1dull;
+            w ^= w >> 29;
+            // exponent of r2 in [26, 253] (2^-101 .. 2^126), of m in [67, 186] (2^-60 .. 2^59)
+            const uint32_t e_r = 26u + static_cast<uint32_t>((z >> 40) % 228u), e_m = 67u + static_cast<uint32_t>((w >> 40) % 120u);
+            uint32_t mant_r = static_cast<uint32_t>(z) & 0x7fffffu, mant_m = static_cast<uint32_t>(w) & 0x7fffffu;
+            const uint32_t kind = static_cast<uint32_t>(z >> 60);
+            if (kind == 0) mant_r = 0x7fffffu - (mant_r & 0xffu);          // just below a power of two
+            if (kind == 1) mant_r &= 0xffu;                                // just above
+            if (kind == 2) mant_m = 0x7fffffu - (mant_m & 0xffu);
+            if (kind == 3) mant_m &= 0xffu;
+            r2 = __uint_as_float((e_r << 23) | mant_r);
+            m = __uint_as_float((e_m << 23) | mant_m | ((static_cast<uint32_t>(w >> 62) & 1u) << 31));
+            if (kind == 4) m = 0.0f;
+        }
+        if (!exact_r2_safe(r2) || !exact_mass_safe(m)) {
+            ++bad;          // the generator must stay inside the window
+            continue;
+        }
+        const float want = __fdiv_rn(m, __fsqrt_rn(r2));
+        const float got = exact_term_fast(m, r2);
+        if (__float_as_uint(want) != __float_as_uint(got)) ++bad;
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
+cudaError_t potential_selftest_exact(int64_t n_random, uint64_t seed, unsigned long long *d_mismatch, int sm_count,
+                                     cudaStream_t stream)
+{
+    k_selftest_exact<<<sm_count * 8, 256, 0, stream>>>(n_random, seed, d_mismatch);
+    return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(kPotentialBlock, 4) k_potential_exact(const PotParams p)

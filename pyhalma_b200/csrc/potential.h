@@ -20,5 +20,9 @@ int potential_group_size(int mode, int variant);
 // Sets the dynamic shared-memory attribute and returns resident blocks per SM.
 cudaError_t potential_configure(int mode, int variant, int *blocks_per_sm);
 cudaError_t potential_launch(const PotParams &p, int mode, int variant, int grid_blocks, cudaStream_t stream);
+// Device self-test of the EXACT kernel's branch-free sqrt / divide against the IEEE library
+// routines; *d_mismatch (zeroed by the caller) receives the number of differing results.
+cudaError_t potential_selftest_exact(int64_t n_random, uint64_t seed, unsigned long long *d_mismatch, int sm_count,
+                                     cudaStream_t stream);
 
 }  // namespace halma

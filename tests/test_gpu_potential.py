@@ -156,3 +156,43 @@ def test_nan_inf_semantics_exact():
     assert out[0] == f32(1.0) / np.sqrt(f32(83.0))
     out = gpu([1.0], [np.inf], [1.0], [1.0], [0.0], [0.0], [0.0], "exact")
     assert out[0] == 0.0
+
+
+def test_exact_branch_free_arithmetic_selftest():
+    """EXACT mode's branch-free rn(m / rn(sqrt(r2))) against the IEEE library routines on the device:
+    every float32 mantissa x exponent parity of r2, and 6e10 pseudo-random operand pairs over the
+    safe window (biased to mantissas next to powers of two and to zero masses)."""
+    import ctypes as C
+    from pyhalma_b200 import _lib
+    for seed in (1, 20240215, 987654321, 55):
+        n = C.c_int64(-1)
+        _lib.check(_lib.lib().halma_selftest_exact_arith(0, 15_000_000_000, seed, C.byref(n)))
+        assert n.value == 0
+
+
+def test_exact_outside_the_safe_window_falls_back_bit_exactly():
+    """Masses and separations outside the window of the branch-free sequence (tiny, huge, subnormal
+    r^2, zero and negative masses) take the IEEE path quad by quad: still bit-identical to the oracle."""
+    rng = np.random.default_rng(77)
+    n = 700
+    x = 3.0 + rng.normal(0, 1e-3, n)
+    y = -7.0 + rng.normal(0, 1e-3, n)
+    z = 11.0 + rng.normal(0, 1e-3, n)
+    m = rng.uniform(0.5e6, 2e6, n)
+    m[::7] = 1e-30
+    m[3::11] = 1e30
+    m[5::13] = 0.0
+    m[6::17] = -1e6
+    m[9::19] = 1e-42          # subnormal mass
+    # sources at subnormal and huge separations from the targets at the origin
+    xs = np.concatenate((x, [1e-22, -3e-21, 1e19, 2e-19]))
+    ys = np.concatenate((y, [2e-22, 1e-21, -1e19, 1e-19]))
+    zs = np.concatenate((z, [-1e-22, 2e-21, 1e19, 3e-19]))
+    ms = np.concatenate((m, [1.0, 2.0, 1e6, 5.0]))
+    tx = np.concatenate((x[:300], [0.0, 0.0]))
+    ty = np.concatenate((y[:300], [0.0, 0.0]))
+    tz = np.concatenate((z[:300], [0.0, 0.0]))
+    out = gpu(ms, xs, ys, zs, tx, ty, tz, "exact")
+    ref = ora(ms, xs, ys, zs, tx, ty, tz, "f32seq")
+    assert np.array_equal(bits(out), bits(ref))
+    assert np.isinf(out[-1]) or out[-1] > 1e20          # the subnormal separations really were exercised
