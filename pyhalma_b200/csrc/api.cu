@@ -473,6 +473,8 @@ struct halma_plan {
     DBuf<int32_t> d_hint;                 // per-halo int arrays: 9 * n_halo + (n_halo + 1)
     DBuf<double> d_hdbl;                  // per-halo doubles: M(1) vb(3) vb_next(3) com(3)
     DBuf<unsigned long long> d_pairs;
+    DBuf<double> d_phi_sym;
+    bool sym = false;
     DBuf<int32_t> d_cint;                 // per-chunk ints: cnt, off
     DBuf<double> d_csum;                  // kChunkSums per chunk
     DBuf<float> d_cbest;
@@ -517,7 +519,7 @@ struct halma_plan {
         d_halo.release(); d_chunk_halo.release(); d_chunk_p0.release(); d_order.release();
         d_ext_off.clear();
         d_in.release(); d_ext.release(); d_stage.release(); d_vb_user.release(); d_work.release();
-        d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_cint.release();
+        d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_cint.release(); d_phi_sym.release();
         d_csum.release(); d_flag.release(); d_mask.release(); d_be.release(); d_E.release();
         d_idx.release(); d_phi.release(); d_st.release();
         d_cbest.release(); d_cbestq.release(); d_hbest.release(); d_hrps.release(); d_temp.release();
@@ -806,6 +808,13 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
         const SortedAxisMut &A = P->sax[a];
         L.ax[a] = SortedAxis{A.x, A.y, A.z, A.m, A.key, A.slot, A.tgt, A.inv, A.corr};
     }
+    // symmetric self-term: rides on the predicate-free kernel's throughput shape (128-member tiles),
+    // one GPU, host-enqueued loop (the per-pass memset of phi_sym is not part of the graph body)
+    P->sym = cfg.symmetric && P->np && cfg.n_ranks == 1 && !cfg.use_graph && P->variant == 0 &&
+             potential_group_size(cfg.mode, P->variant) == 128;
+    if (P->sym) CU_TRY(P->d_phi_sym.alloc(NP));
+    L.phi_sym = P->d_phi_sym.p;
+    L.sym_enabled = P->sym ? 1 : 0;
 
     PotParams &Q = P->pp;
     memset(&Q, 0, sizeof Q);
@@ -832,6 +841,8 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     Q.halo_redo = P->d_redo.p;
     Q.np_enabled = P->np ? 1 : 0;
     Q.redo_only = 0;
+    Q.phi_sym = P->d_phi_sym.p;
+    Q.sym_enabled = P->sym ? 1 : 0;
     for (int a = 0; a < 3 && P->np; ++a) {
         Q.ax[a] = L.ax[a];
         Q.src[3 + a] = F32Set{P->sax[a].x, P->sax[a].y, P->sax[a].z, P->sax[a].m};
@@ -1112,6 +1123,7 @@ static int enqueue_pass(halma_plan *P, int pass)
     CU_TRY(cudaEventRecord(P->ev[3 * pass], s));
     if (P->np && P->cfg.n_ranks > 1)      // split mode: every correction entry is written by one rank only
         CU_TRY(cudaMemsetAsync(P->d_corr.p, 0, 3 * static_cast<size_t>(P->n_pad) * sizeof(double), s));
+    if (P->sym) CU_TRY(cudaMemsetAsync(P->d_phi_sym.p, 0, static_cast<size_t>(P->n_pad) * sizeof(double), s));
     CU_TRY(potential_launch(P->pp, P->cfg.mode, P->variant, grid, s));
     if (P->np) {
         // haloes whose predicate-free sums came out non-finite are recomputed with the predicate

@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
             const int S = p.nsplit[h];
             double phi = p.phi_part[i];
             for (int k = 1; k < S; ++k) phi += p.phi_part[static_cast<int64_t>(k) * p.n_pad + i];
+            if (p.sym_enabled && !p.halo_redo[h]) phi += p.phi_sym[i];
             if (p.np_enabled && !p.halo_redo[h]) {
                 // predicate-free path: take out the pairs that share a coordinate (potential.cu)
                 const int64_t slot = hd.poff + (g - hd.uoff);
@@ -465,6 +466,11 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
                 items = my_groups(n, p.group_size, p.rank, p.n_ranks) * S;
                 // correction tickets: three axes x blocks of the (static) sorted member list
                 if (p.np_enabled) items += 3 * my_groups(p.halo[h].n0, p.group_size, p.rank, p.n_ranks);
+                // symmetric tickets: row tiles x chunks of column tiles (potential.cu::decode_ticket)
+                if (p.sym_enabled) {
+                    const int tiles = (n + p.group_size - 1) / p.group_size;
+                    if (tiles >= 2) items += tiles * ((tiles - 1 + kSymChunkTiles - 1) / kSymChunkTiles);
+                }
             }
         }
         // inclusive warp scan

@@ -52,6 +52,9 @@ struct LoopParams {
     SortedAxis ax[3];
     int32_t *halo_redo;
     int32_t np_enabled;
+    // symmetric self-term (potential.cu::sym_ticket): off-diagonal member x member sums
+    const double *phi_sym;                // [n_pad]
+    int32_t sym_enabled;
     // CUDA-graph loop driver: conditional handle of the WHILE node (0 = not in a graph)
     unsigned long long cond_handle;
 };

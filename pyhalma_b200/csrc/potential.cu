@@ -48,7 +48,8 @@ constexpr int kFlushQuads = 8;              // flush float32 partials every 8 qu
 constexpr int kFlushQuadsNp = 16;           // ... or 64 in the predicate-free body, whose packed accumulator
                                             // keeps even and odd sources apart (32 terms per float32 sum)
 constexpr int kWarpsPerBlock = kPotentialBlock / 32;
-constexpr int kSmemBytes = kWarpsPerBlock * kStages * (kStageFloats * 4 + 8);
+// ring stages + their mbarriers + the column partial sums of the symmetric tickets
+constexpr int kSmemBytes = kWarpsPerBlock * (kStages * (kStageFloats * 4 + 8) + kTileJ * 4);
 
 // ---------------------------------------------------------------------------------------
 // Cursor over the source tiles of one ticket.  Main tickets: piece `s` of `S` of every
@@ -60,6 +61,7 @@ struct TileCursor {
     int nseg, k, S, s, n_members, parity;
     int64_t base;
     int set, pos, end, flags;
+    int own_tile;       // >= 0: symmetric mode, the members segment is only this tile (taken by split 0)
 
     __device__ __forceinline__ void seek()
     {
@@ -67,8 +69,12 @@ struct TileCursor {
             const SegDesc sd = hd->seg[k];
             const int c = (sd.flags & kSegMembers) ? n_members : sd.count;
             const int per = (((c + S - 1) / S) + kTileJ - 1) / kTileJ * kTileJ;
-            const int a = s * per;
-            const int b = min(a + per, c);
+            int a = s * per;
+            int b = min(a + per, c);
+            if ((sd.flags & kSegMembers) && own_tile >= 0) {
+                a = s == 0 ? own_tile * kTileJ : c;
+                b = min(a + kTileJ, c);
+            }
             if (a < b) {
                 base = sd.begin;
                 set = (sd.flags & kSegMembers) ? parity : 2;
@@ -80,8 +86,10 @@ struct TileCursor {
             ++k;
         }
     }
-    __device__ __forceinline__ void init(const HaloDesc *h, int S_, int s_, int n_members_, int parity_)
+    __device__ __forceinline__ void init(const HaloDesc *h, int S_, int s_, int n_members_, int parity_,
+                                         int own_tile_ = -1)
     {
+        own_tile = own_tile_;
         hd = h;
         nseg = h->nseg;
         k = 0;
@@ -93,6 +101,7 @@ struct TileCursor {
     }
     __device__ __forceinline__ void init_range(int set_, int64_t begin, int count)
     {
+        own_tile = -1;
         hd = nullptr;
         nseg = 1;
         k = count > 0 ? 0 : 1;
@@ -161,7 +170,8 @@ __device__ __forceinline__ void issue_tile(const PotParams &p, const TileCursor 
 // ---------------------------------------------------------------------------------------
 struct Ticket {
     int h, group, s, S, n_tgt;
-    int corr_axis;      // -1: main ticket; 0..2: correction ticket of that axis, `group` = block
+    int corr_axis;      // -1: main ticket; 0..2: correction ticket of that axis, `group` = block;
+                        // 3: symmetric ticket, `group` = row tile, `s` = chunk of column tiles
 };
 
 // Ticket layout of a halo (must match loop_kernels.cu::k_schedule):
@@ -198,10 +208,20 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
     // correction blocks are dealt round-robin to the ranks like the target groups
     const int nblk = (p.halo[t.h].n0 + kGroup - 1) / kGroup;
     const int myblk = (nblk - p.rank + p.n_ranks - 1) / p.n_ranks;
-    if (myblk <= 0 || local >= 3 * myblk) return false;
-    t.corr_axis = local / myblk;
-    t.group = (local % myblk) * p.n_ranks + p.rank;
-    t.s = 0;
+    if (myblk > 0 && local < 3 * myblk) {
+        t.corr_axis = local / myblk;
+        t.group = (local % myblk) * p.n_ranks + p.rank;
+        t.s = 0;
+        return true;
+    }
+    if (!p.sym_enabled || groups < 2) return false;
+    // symmetric tickets: (row tile I, chunk c of the tiles J > I); ids of empty chunks are skipped
+    local -= 3 * max(myblk, 0);
+    const int chunks = (groups - 1 + kSymChunkTiles - 1) / kSymChunkTiles;
+    if (local >= groups * chunks) return false;
+    t.corr_axis = 3;
+    t.group = local / chunks;
+    t.s = local % chunks;
     return true;
 }
 
@@ -413,7 +433,148 @@ __device__ __forceinline__ void correction_ticket(const PotParams &p, const Tick
         if (slot[t] >= 0) A.corr[slot[t]] = acc64[t];
 }
 
-template <int T, int MINB, bool NP>
+// ---------------------------------------------------------------------------------------
+// Symmetric tickets (opt-in, halma_unbind_config.symmetric).  A pair of members in different
+// tiles is evaluated ONCE: m_j / r goes to the row particle's sum, m_i / r to the column
+// particle's.  Half the MUFU.RSQ work for the member x member term.
+// The warp holds the 128 members of row tile I in registers (4 per lane) and streams column
+// tiles J > I through the TMA ring.  Inside a tile lanes sweep the 64 source PAIRS in rotation
+// (lane l visits pair (k + l) mod 64 at step k), so the column partial sums live in shared memory
+// as plain read-modify-writes without conflicts.  Row and column sums are added to phi_sym with
+// float64 atomics: their order is not fixed, so a symmetric run is reproducible to ~1e-16 of the
+// potential (before its float32 rounding), not bit for bit -- which is why the mode is opt-in.
+// scripts/probes/symmetric_probe.cu: 3.4-3.5 T pair evaluations/s = 6.8-7.1 T interactions/s.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sym_tile(const float *__restrict__ stage, float *__restrict__ col, const float (&xi)[4],
+                                         const float (&yi)[4], const float (&zi)[4], const float (&mi)[4],
+                                         double (&acc64)[4], int lane)
+{
+    const uint64_t *X = reinterpret_cast<const uint64_t *>(stage);
+    const uint64_t *Y = reinterpret_cast<const uint64_t *>(stage + kTileJ);
+    const uint64_t *Z = reinterpret_cast<const uint64_t *>(stage + 2 * kTileJ);
+    const uint64_t *M = reinterpret_cast<const uint64_t *>(stage + 3 * kTileJ);
+    uint64_t *C2 = reinterpret_cast<uint64_t *>(col);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {          // row partials: 32 terms per float32 sum, then float64
+        uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll 2
+        for (int k = half * 32; k < half * 32 + 32; ++k) {
+            const int j = (k + lane) & (kTileJ / 2 - 1);
+            const uint64_t x01 = X[j], y01 = Y[j], z01 = Z[j], m01 = M[j];
+            uint64_t c2 = 0ull;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint64_t dx = sub2(x01, pack2(xi[t], xi[t]));
+                const uint64_t dy = sub2(y01, pack2(yi[t], yi[t]));
+                const uint64_t dz = sub2(z01, pack2(zi[t], zi[t]));
+                const uint64_t r2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                float r20, r21;
+                unpack2(r2, r20, r21);
+                const uint64_t inv = pack2(rsqrt_ftz(r20), rsqrt_ftz(r21));
+                acc2[t] = fma2(m01, inv, acc2[t]);
+                c2 = fma2(pack2(mi[t], mi[t]), inv, c2);
+            }
+            float c_lo, c_hi, o_lo, o_hi;
+            unpack2(c2, c_lo, c_hi);
+            unpack2(C2[j], o_lo, o_hi);
+            C2[j] = pack2(o_lo + c_lo, o_hi + c_hi);
+            __syncwarp();          // the next step hands pair j to the neighbouring lane
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float lo, hi;
+            unpack2(acc2[t], lo, hi);
+            acc64[t] += static_cast<double>(lo + hi);
+        }
+    }
+}
+
+__device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk, Ring &rg, float *col, int lane,
+                                           int parity)
+{
+    const HaloDesc *hd = &p.halo[tk.h];
+    const int n = tk.n_tgt;
+    const int G = (n + kTileJ - 1) / kTileJ;
+    const int I = tk.group;
+    const int j0 = I + 1 + tk.s * kSymChunkTiles;
+    if (j0 >= G) return;                              // an empty chunk of this row
+    const int j1 = min(j0 + kSymChunkTiles, G);
+    const F32Set sp = p.src[parity];
+    const int64_t base = hd->poff;
+    float xi[4], yi[4], zi[4], mi[4];
+    double acc64[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {                     // row tile I < G - 1 is always full
+        const int64_t i = base + I * kTileJ + t * 32 + lane;
+        xi[t] = sp.x[i];
+        yi[t] = sp.y[i];
+        zi[t] = sp.z[i];
+        mi[t] = sp.m[i];
+        acc64[t] = 0.0;
+    }
+    bool bad = false;
+    TileCursor prod;
+    prod.init_range(parity, base + static_cast<int64_t>(j0) * kTileJ, min(n, j1 * kTileJ) - j0 * kTileJ);
+    TileCursor cons = prod;
+#pragma unroll 1
+    for (int i = 0; i < kStages - 1 && prod.valid(); ++i) {
+        issue_tile(p, prod, rg.buf + rg.fill * kStageFloats, &rg.bars[rg.fill], lane);
+        rg.fill = (rg.fill + 1 == kStages) ? 0 : rg.fill + 1;
+        prod.next();
+    }
+#pragma unroll 1
+    while (cons.valid()) {
+        if (prod.valid()) {
+            issue_tile(p, prod, rg.buf + rg.fill * kStageFloats, &rg.bars[rg.fill], lane);
+            rg.fill = (rg.fill + 1 == kStages) ? 0 : rg.fill + 1;
+            prod.next();
+        }
+        mbar_wait(&rg.bars[rg.use], (rg.par >> rg.use) & 1u);
+        rg.par ^= 1u << rg.use;
+        float *stage = rg.buf + rg.use * kStageFloats;
+        const int len = cons.len();
+        if (len < kTileJ) {
+            // the rotation visits all 64 pairs: fill the rest of a short last tile with sources at
+            // infinity and mass 0, which contribute exactly zero to rows and columns
+            for (int e = ((len + 3) & ~3) + lane; e < kTileJ; e += 32) {
+                stage[e] = __int_as_float(0x7f800000);
+                stage[kTileJ + e] = __int_as_float(0x7f800000);
+                stage[2 * kTileJ + e] = __int_as_float(0x7f800000);
+                stage[3 * kTileJ + e] = 0.f;
+            }
+            fence_proxy_async_smem();
+        }
+#pragma unroll
+        for (int e = lane; e < kTileJ; e += 32) col[e] = 0.f;
+        __syncwarp();
+        sym_tile(stage, col, xi, yi, zi, mi, acc64, lane);
+        __syncwarp();
+        const int64_t tile0 = cons.base + cons.pos;
+#pragma unroll
+        for (int e = lane; e < kTileJ; e += 32)
+            if (e < len) {
+                const float v = col[e];
+                bad |= !(fabsf(v) <= 3.4028234e38f);
+                atomicAdd(&p.phi_sym[tile0 + e], static_cast<double>(v));
+            }
+        __syncwarp();      // every lane is done with this stage and with col before they are reused
+        rg.use = (rg.use + 1 == kStages) ? 0 : rg.use + 1;
+        cons.next();
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        bad |= !(fabs(acc64[t]) <= 1.7976931348623157e308);
+        atomicAdd(&p.phi_sym[base + I * kTileJ + t * 32 + lane], acc64[t]);
+    }
+    // a zero separation between different tiles (exact duplicates) or non-finite input: the
+    // predicated kernel recomputes the halo from scratch and phi_sym is ignored for it
+    if (__any_sync(0xffffffffu, bad) && lane == 0) {
+        atomicExch(&p.halo_redo[tk.h], 1);
+        atomicExch(&p.st->redo_any, 1);
+    }
+}
+
+template <int T, int MINB, bool NP, bool SYM = false>
 __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const PotParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -426,6 +587,8 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
     rg.bars = reinterpret_cast<uint64_t *>(smem_raw + kWarpsPerBlock * kStages * kStageFloats * 4) + warp * kStages;
     rg.par = 0;
     rg.fill = rg.use = 0;
+    float *col = reinterpret_cast<float *>(smem_raw + kWarpsPerBlock * kStages * (kStageFloats * 4 + 8)) + warp * kTileJ;
+    static_assert(!SYM || (NP && T == 4), "symmetric tickets use 128-member tiles on the predicate-free kernel");
     if (lane == 0) {
         for (int i = 0; i < kStages; ++i) mbar_init(&rg.bars[i], 1);
         fence_mbar_init();
@@ -444,6 +607,10 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
         if (item >= n_items) break;
         Ticket tk;
         if (!decode_ticket<kGroup>(p, item, tk)) continue;
+        if (tk.corr_axis == 3) {
+            if (SYM) sym_ticket(p, tk, rg, col, lane, parity);
+            continue;
+        }
         if (tk.corr_axis >= 0) {
             if (NP) {
                 if (tk.corr_axis == 0)
@@ -472,7 +639,7 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
             acc64[t] = 0.0;
         }
         TileCursor cur;
-        cur.init(hd, tk.S, tk.s, tk.n_tgt, parity);
+        cur.init(hd, tk.S, tk.s, tk.n_tgt, parity, SYM ? tk.group : -1);
         if (NP) {
             run_tiles<T, 1>(p, cur, rg, lane, tk.group * kGroup, tk.group * kGroup + kGroup, xi, yi, zi, acc64);
             // zero separations outside the own tile (exact duplicates) or non-finite input:
@@ -720,6 +887,12 @@ const FastVariant kVariants[] = {
 #undef HALMA_VARIANT
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
+// The kernel that also runs the symmetric tickets: the throughput shape with room for the extra
+// registers of the two-sided body (128 per thread, 4 blocks per SM).
+const auto kSymKernel = k_potential_fast<4, 4, true, true>;
+int g_bps[16] = {0};
+int g_sym_bps = 0;
+
 int forced_variant()
 {
     static int idx = [] {
@@ -768,6 +941,12 @@ cudaError_t potential_configure(int mode, int variant, int *blocks_per_sm)
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, v.np, kPotentialBlock, kSmemBytes);
     *blocks_per_sm = a < b ? a : b;
+    if (variant < 16) g_bps[variant] = *blocks_per_sm;
+    if (e == cudaSuccess && variant == 0) {
+        e = cudaFuncSetAttribute(kSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sym_bps, kSymKernel, kPotentialBlock, kSmemBytes);
+    }
     return e;
 }
 
@@ -775,7 +954,10 @@ cudaError_t potential_launch(const PotParams &p, int mode, int variant, int grid
 {
     if (mode == HALMA_MODE_EXACT)
         k_potential_exact<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
-    else if (p.np_enabled && !p.redo_only)
+    else if (p.np_enabled && !p.redo_only && p.sym_enabled) {
+        const int per_sm = variant < 16 && g_bps[variant] > 0 ? g_bps[variant] : 1;
+        kSymKernel<<<grid_blocks / per_sm * (g_sym_bps > 0 ? g_sym_bps : 1), kPotentialBlock, kSmemBytes, stream>>>(p);
+    } else if (p.np_enabled && !p.redo_only)
         kVariants[variant].np<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else
         kVariants[variant].pred<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);

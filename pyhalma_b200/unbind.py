@@ -104,7 +104,7 @@ class UnbindPlan:
     def __init__(self, offsets, ext_offsets: Sequence = (), *, mode="fast", n_pre: int = 0,
                  split_classes: bool = False, vb_fixed: bool = False, max_iter: int = 64,
                  G: float = G_CONST, kappa: float = 9.0, device: int = 0, rank: int = 0, n_ranks: int = 1,
-                 use_graph: Optional[bool] = None):
+                 use_graph: Optional[bool] = None, symmetric: Optional[bool] = None):
         L = _lib.lib()
         self._L = L
         self.offsets = _i64(offsets)
@@ -135,6 +135,10 @@ class UnbindPlan:
             import os
             use_graph = os.environ.get("HALMA_GRAPH", "0") not in ("0", "")
         cfg.use_graph = int(bool(use_graph))
+        if symmetric is None:
+            import os
+            symmetric = os.environ.get("HALMA_SYMMETRIC", "0") not in ("0", "")
+        cfg.symmetric = int(bool(symmetric))
         self.cfg = cfg
         ptrs = (C.POINTER(C.c_int64) * max(1, len(self.ext_offsets)))()
         for g, e in enumerate(self.ext_offsets):
@@ -283,15 +287,17 @@ def nccl_unique_id() -> bytes:
 def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (), n_pre: int = 0,
                      split_classes: bool = False, vb=None, kappa: float = 9.0, max_iter: int = 64,
                      mode="fast", device: int = 0, G: float = G_CONST, temp=None,
-                     cold_T: float = 5 * 1e4) -> CatalogueResult:
+                     cold_T: float = 5 * 1e4, symmetric: Optional[bool] = None) -> CatalogueResult:
     """Unbind every halo of a catalogue in one batched, device-resident run.
 
     groups: sequence of (ext_offsets, mass, x, y, z) external source groups.
     vb: None (bulk velocity recomputed from the bound set each pass) or float64[n_halo, 3].
     temp: optional member temperatures; fills the cold / hot mass sums of every HaloResult.
+    symmetric: evaluate member x member pairs once for both particles (halma_unbind_config.symmetric).
     """
     plan = UnbindPlan(offsets, [g[0] for g in groups], mode=mode, n_pre=n_pre, split_classes=split_classes,
-                      vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa, device=device)
+                      vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa, device=device,
+                      symmetric=symmetric)
     try:
         plan.upload_members(x, y, z, vx, vy, vz, mass)
         for k, g in enumerate(groups):
@@ -310,7 +316,7 @@ def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (
 
 def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence = (),
                 split_classes: bool = False, kappa: float = 9.0, vb_fixed=None, max_iter: int = 64,
-                mode="fast", device: int = 0, G: float = G_CONST) -> UnbindResult:
+                mode="fast", device: int = 0, G: float = G_CONST, symmetric: Optional[bool] = None) -> UnbindResult:
     """One halo.  pre / post: sequences of (mass, x, y, z) fixed source groups summed before /
     after the members (same keywords as oracle.unbind_halo)."""
     n = len(x)
@@ -319,7 +325,7 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence
     res = unbind_catalogue(np.array([0, n], np.int64), x, y, z, vx, vy, vz, mass, groups=groups,
                            n_pre=len(pre), split_classes=split_classes,
                            vb=None if vb_fixed is None else np.asarray(vb_fixed, np.float64).reshape(1, 3),
-                           kappa=kappa, max_iter=max_iter, mode=mode, device=device, G=G)
+                           kappa=kappa, max_iter=max_iter, mode=mode, device=device, G=G, symmetric=symmetric)
     h = res.halos[0]
     return UnbindResult(res.mask.astype(bool), res.members(0).astype(np.int64), res.be32, res.energy, h.n_iter,
                         h.mass, h.com, h.vb, h.pairs, h.converged, res.stats)

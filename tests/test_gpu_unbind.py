@@ -531,3 +531,59 @@ def test_predicate_free_path_forced_on_small_and_odd_inputs():
                           "-m", "gpu", "-k", sel], capture_output=True, text=True, timeout=1200, env=env, cwd=root)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout
+
+
+def test_symmetric_self_term_against_one_sided_and_oracle():
+    """halma_unbind_config.symmetric: member x member pairs of different tiles are evaluated once for
+    both particles.  Same predicate, same per-pair arithmetic; only the order of the float64 partial
+    sums differs, so potentials agree with the one-sided kernel and with the float64 oracle within
+    the FAST tolerance (1e-6) and masks outside the 1e-6 energy band."""
+    rng = np.random.default_rng(123)
+    n = 70_000                                    # 4.9e9 member pairs: predicate-free kernel, throughput shape
+    st = synth.plummer_stars(n, 6 * synth.KPC, 1e6, rng)
+    synth.add_coincident_pairs(st, 5, rng)        # shared coordinates -> correction tickets
+    gas = synth.lattice_gas(4000, synth.CELL, rng, m_total=5e9)
+    dm = synth.dm_cloud(3000, 20 * synth.KPC, 1e7, rng)
+    kw = dict(pre=[gas.pos_mass()], post=[dm.pos_mass()], kappa=9.0)
+    args = (st.x, st.y, st.z, st.vx, st.vy, st.vz, st.mass)
+    one = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, **kw)
+    sym = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=True, **kw)
+    ref = O.unbind_halo(*args, variant="f64acc", max_iter=1, vb_fixed=synth.BULK_V, **kw)
+    np.testing.assert_allclose(sym.be32, ref.be32, rtol=1e-6)
+    np.testing.assert_allclose(sym.be32, one.be32, rtol=1e-6)
+    assert np.max(np.abs(sym.be32.astype(np.float64) / ref.be32 - 1)) < 5e-7
+    diff = sym.mask != ref.mask
+    assert np.all(O.energy_margin(ref.energy, ref.be32, 9.0)[diff] < 1e-6)
+    assert sym.pairs == one.pairs                  # interactions are counted the same way
+    # iterated to the fixed point: same member set as the one-sided run (up to the energy band)
+    one = unbind_halo(*args, mode="fast", **kw)
+    sym = unbind_halo(*args, mode="fast", symmetric=True, **kw)
+    assert sym.n_iter == one.n_iter and np.count_nonzero(sym.mask != one.mask) <= 2
+    np.testing.assert_allclose(sym.mass, one.mass, rtol=1e-4)
+    # exact duplicates in DIFFERENT tiles: the symmetric sums come out non-finite and the halo is
+    # recomputed by the predicated kernel, like in the one-sided predicate-free path
+    x2 = st.x.copy(); y2 = st.y.copy(); z2 = st.z.copy()
+    x2[60_000], y2[60_000], z2[60_000] = x2[17], y2[17], z2[17]
+    a2 = (x2, y2, z2, st.vx, st.vy, st.vz, st.mass)
+    one = unbind_halo(*a2, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, **kw)
+    sym = unbind_halo(*a2, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=True, **kw)
+    assert np.all(np.isfinite(sym.be32))
+    np.testing.assert_array_equal(sym.be32, one.be32)          # both took the same fallback
+
+
+def test_symmetric_mode_forced_on_small_and_odd_inputs():
+    """The same battery as the predicate-free path, with symmetric tickets on and the throughput
+    shape forced so that small and ragged haloes go through them (haloes of <= 128 members have
+    no off-diagonal tile and must be unaffected)."""
+    import subprocess
+    import sys
+    if os.environ.get("HALMA_SYMMETRIC") == "1":
+        pytest.skip("already running in symmetric mode")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HALMA_NP_MIN_PAIRS="0", HALMA_SYMMETRIC="1", HALMA_FAST_VARIANT="0")
+    sel = ("ragged or degenerate or duplicates or zero_mass or external_groups or golden_fast or fused_large "
+           "or fast_mode_against or lattice or rps_mass_sums or cfg3_full or cfg2_full")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_unbind.py"), "-q", "-x",
+                          "-m", "gpu", "-k", sel], capture_output=True, text=True, timeout=1500, env=env, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout
