@@ -16,7 +16,11 @@ count.
   e2e       the same through the public one-shot API with pinned HOST buffers: H2D of every
             input and D2H of mask + potentials + energies + member lists inside the timing
   roofline  the potential kernel alone against the MUFU.RSQ issue roofline
-            (16 interactions / clk / SM nominal; the rate and the SM clock are measured)
+            (16 rsqrt / clk / SM nominal; the rate and the SM clock are measured), in 1/r
+            EVALUATIONS per second.  With --symmetric 1 (default) a member pair in different tiles
+            is evaluated once and serves both particles, so there are fewer evaluations than
+            interactions; `one_sided` repeats the measurement with --symmetric 0, where the two
+            are the same number
   cpu_baseline  the C/OpenMP oracle (a port of the Fortran kernel, oracle/) on the host cores
 
 --impl reference times that CPU port alone, with all host threads, on a bounded sample of
@@ -128,13 +132,17 @@ def shared_comm(rank, world, device):
     return _COMM["c"]
 
 
-def make_plan(job, mode, device, rank=0, world=1, upload=True):
+SYMMETRIC = True      # set from --symmetric
+
+
+def make_plan(job, mode, device, rank=0, world=1, upload=True, symmetric=None):
     from pyhalma_b200.unbind import UnbindPlan
     kw = job["kw"]
     split = job["split"] and world > 1
     plan = UnbindPlan(job["offsets"], [g[0] for g in job["groups"]], mode=mode, n_pre=kw["n_pre"],
                       split_classes=kw["split_classes"], vb_fixed=kw["vb"] is not None, max_iter=64,
-                      kappa=kw["kappa"], device=device, rank=rank if split else 0, n_ranks=world if split else 1)
+                      kappa=kw["kappa"], device=device, rank=rank if split else 0, n_ranks=world if split else 1,
+                      symmetric=SYMMETRIC if symmetric is None else symmetric)
     if split:
         plan.use_comm(shared_comm(rank, world, device))
     if upload:
@@ -324,7 +332,7 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     dev_ms = pot_ms = 0.0
-    pairs = launches = pot_launches = passes = 0
+    pairs = evals = launches = pot_launches = passes = 0
     busy_windows = []
     for _ in range(args.steps):
         tb = time.perf_counter()
@@ -333,6 +341,7 @@ def run_gpu(args, rank, local_rank, world):
             pot_ms += st.potential_ms
             # in split mode every rank's counter covers the whole halo: count it once
             pairs += st.pairs // world if (job["split"] and world > 1) else st.pairs
+            evals += st.evaluations // world if (job["split"] and world > 1) else st.evaluations
             launches += st.launches
             pot_launches += st.potential_launches
             passes += st.passes
@@ -358,6 +367,25 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     e2e_s = time.perf_counter() - te0
 
+    # the same workload with one-sided sums only (symmetric = 0): evaluations == interactions
+    one_sided = None
+    if SYMMETRIC:
+        for p in plans:
+            p.close()
+        plans = [make_plan(j, mode, local_rank, rank, world, symmetric=False) for j in jobs]
+        step()
+        barrier()
+        o_ms = o_pot = 0.0
+        o_pairs = 0
+        o_steps = max(1, min(args.steps, 2))
+        for _ in range(o_steps):
+            for st, job in zip(step(), jobs):
+                o_ms += st.total_ms
+                o_pot += st.potential_ms
+                o_pairs += st.pairs // world if (job["split"] and world > 1) else st.pairs
+        barrier()
+        one_sided = (o_ms, o_pot, o_pairs, o_steps)
+
     # reduce over ranks: max time, sum of work
     t = torch.tensor([dev_ms, wall_ms, e2e_s, pot_ms], dtype=torch.float64, device="cuda")
     w = torch.tensor([pairs, e2e_pairs, launches], dtype=torch.float64, device="cuda")
@@ -376,7 +404,7 @@ def run_gpu(args, rank, local_rank, world):
         value = pairs_all / (dev_ms_max * 1e-3) / 1e9
         # roofline of the dominant kernel (rank 0's launches)
         # rank 0's share of the work (already divided in split mode) over rank 0's kernel time
-        pot_rate = pairs / (pot_ms * 1e-3) / 1e9
+        pot_rate = evals / (pot_ms * 1e-3) / 1e9
         sm_mhz = clocks.get("sm_mhz") or mb["sm_clock_mhz"]
         peak = mb["rsq_per_clk_sm"] * mb["sm_count"] * sm_mhz * 1e6 / 1e9
         n_src = [len(j["members"][0]) + sum(len(g[1]) for g in j["groups"]) for j in jobs]
@@ -385,7 +413,9 @@ def run_gpu(args, rank, local_rank, world):
         alg_bytes_first_pass = sum(16 * s * 4 + 20 * t_ + 24 * t_ for s, t_ in zip(n_src, n_tgt))
         roofline = {
             "bound": "mufu", "kernel": "k_potential_fast" if mode == "fast" else "k_potential_exact",
-            "achieved": pot_rate, "peak": peak, "unit": UNIT, "frac": pot_rate / peak,
+            "achieved": pot_rate, "peak": peak, "unit": "G 1/r evaluations/s (one MUFU.RSQ each)", "frac": pot_rate / peak,
+            "interactions_per_evaluation": pairs / max(evals, 1),
+            "achieved_interactions": pairs / (pot_ms * 1e-3) / 1e9,
             "peak_how": "measured: MUFU.RSQ/clk/SM from halma_microbench (%.2f) x %d SMs x median SM clock sampled "
                         "during the timed region (%.0f MHz)" % (mb["rsq_per_clk_sm"], mb["sm_count"], sm_mhz),
             "nominal_peak": 16 * mb["sm_count"] * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9,
@@ -419,7 +449,7 @@ def run_gpu(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(desc, mode=mode, l2="flushed between steps (256 MiB write)",
-                           passes_per_step=passes / args.steps),
+                           passes_per_step=passes / args.steps, symmetric_self_term=bool(SYMMETRIC)),
             "wall_ms_per_step": wall_ms_max / args.steps,
             "interactions_per_step": pairs_all / args.steps,
             "clocks": clocks,
@@ -428,6 +458,12 @@ def run_gpu(args, rank, local_rank, world):
                     "how": "public plan API per job, everything inside the timing: plan create + H2D from pinned "
                            "host + device loop + D2H of mask, potentials, energies, member lists + destroy"},
             "gpu_launches": int(launches_all),
+            "one_sided": None if one_sided is None else {
+                "value": one_sided[2] / (one_sided[0] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": one_sided[0] / one_sided[3],
+                "kernel": one_sided[2] / (one_sided[1] * 1e-3) / 1e9, "roofline_frac": one_sided[2] / (one_sided[1] * 1e-3) / 1e9 / peak,
+                "scope": "rank 0" if world > 1 else "whole job", "steps": one_sided[3],
+                "note": "same workload with halma_unbind_config.symmetric = 0: every interaction is its own 1/r "
+                        "evaluation and results are bit-reproducible"},
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
@@ -448,6 +484,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--symmetric", type=int, default=1, choices=[0, 1],
+                    help="evaluate member x member pairs once for both particles (FAST mode, not in split mode)")
     ap.add_argument("--cpu-targets", type=int, default=60000, help="targets per job in the cpu_baseline sample")
     ap.add_argument("--ref-targets", type=int, default=20000, help="targets per job per step of --impl reference")
     args = ap.parse_args()
@@ -456,6 +494,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    global SYMMETRIC
+    SYMMETRIC = bool(args.symmetric) and args.mode == "fast"
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -163,7 +163,10 @@ typedef struct halma_run_stats {
     int32_t launches;        /* all kernel launches issued by the run                    */
     int32_t passes;          /* loop passes executed (max over haloes)                   */
     int32_t reserved;
-    int64_t pairs;           /* interactions evaluated, summed over haloes and passes    */
+    int64_t pairs;           /* interactions (target, source) summed over haloes and passes:
+                                what the reference's double loop visits                  */
+    int64_t evaluations;     /* 1/r evaluations made for them: = pairs, or fewer with
+                                symmetric = 1 (one evaluation serves both particles)      */
 } halma_run_stats;
 
 /* offsets: int64[n_halo+1], ext_offsets[g]: int64[n_halo+1] for g < n_groups (host). */

@@ -55,7 +55,7 @@ class HaloResult(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("potential_ms", C.c_double),
                 ("potential_launches", C.c_int32), ("launches", C.c_int32), ("passes", C.c_int32),
-                ("reserved", C.c_int32), ("pairs", C.c_int64)]
+                ("reserved", C.c_int32), ("pairs", C.c_int64), ("evaluations", C.c_int64)]
 
 
 _lib = None

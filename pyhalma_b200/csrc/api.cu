@@ -472,7 +472,7 @@ struct halma_plan {
     DBuf<int32_t> d_widx;                 // 2 * n_pad
     DBuf<int32_t> d_hint;                 // per-halo int arrays: 9 * n_halo + (n_halo + 1)
     DBuf<double> d_hdbl;                  // per-halo doubles: M(1) vb(3) vb_next(3) com(3)
-    DBuf<unsigned long long> d_pairs;
+    DBuf<unsigned long long> d_pairs, d_evals;
     DBuf<double> d_phi_sym;
     bool sym = false;
     DBuf<int32_t> d_cint;                 // per-chunk ints: cnt, off
@@ -519,7 +519,7 @@ struct halma_plan {
         d_halo.release(); d_chunk_halo.release(); d_chunk_p0.release(); d_order.release();
         d_ext_off.clear();
         d_in.release(); d_ext.release(); d_stage.release(); d_vb_user.release(); d_work.release();
-        d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_cint.release(); d_phi_sym.release();
+        d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_evals.release(); d_cint.release(); d_phi_sym.release();
         d_csum.release(); d_flag.release(); d_mask.release(); d_be.release(); d_E.release();
         d_idx.release(); d_phi.release(); d_st.release();
         d_cbest.release(); d_cbestq.release(); d_hbest.release(); d_hrps.release(); d_temp.release();
@@ -668,6 +668,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(P->d_hint.alloc(9 * nh + nh + 1));
     CU_TRY(P->d_hdbl.alloc(10 * nh));
     CU_TRY(P->d_pairs.alloc(nh));
+    CU_TRY(P->d_evals.alloc(nh));
     CU_TRY(P->d_cint.alloc(2 * static_cast<size_t>(P->n_chunks)));
     CU_TRY(P->d_csum.alloc(kChunkSums * static_cast<size_t>(P->n_chunks)));
     CU_TRY(P->d_cbest.alloc(static_cast<size_t>(P->n_chunks)));
@@ -768,6 +769,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.hvb_next = hd + 4 * nh;
     L.hcom = hd + 7 * nh;
     L.pairs = P->d_pairs.p;
+    L.evals = P->d_evals.p;
     L.chunk_cnt = P->d_cint.p;
     L.chunk_off = P->d_cint.p + P->n_chunks;
     L.chunk_sum = P->d_csum.p;
@@ -1248,6 +1250,10 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
             unsigned long long t = 0;
             for (auto v : pr) t += v;
             stats->pairs = static_cast<int64_t>(t);
+            CU_TRY(cudaMemcpy(pr.data(), P->d_evals.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            t = 0;
+            for (auto v : pr) t += v;
+            stats->evaluations = static_cast<int64_t>(t);
         }
     }
     return HALMA_OK;

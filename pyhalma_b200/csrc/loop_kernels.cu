@@ -335,12 +335,22 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
                 p.iter[h] = 0;
                 p.converged[h] = (n_new == 0) ? 1 : 0;
                 p.pairs[h] = 0ull;
+                p.evals[h] = 0ull;
                 act = (n_new > 0 && p.max_iter > 0) ? 1 : 0;
             } else {
                 const int it = p.iter[h] + 1;
                 p.iter[h] = it;
-                p.pairs[h] += static_cast<unsigned long long>(n_old) *
-                              static_cast<unsigned long long>(n_old + hd.n_ext);
+                const unsigned long long nn = static_cast<unsigned long long>(n_old);
+                p.pairs[h] += nn * static_cast<unsigned long long>(n_old + hd.n_ext);
+                const unsigned long long tiles = (nn + p.group_size - 1) / p.group_size;
+                if (p.sym_enabled && tiles >= 2 && !p.halo_redo[h]) {
+                    // diagonal tiles one-sided, every other member pair once
+                    const unsigned long long last = nn - (tiles - 1) * p.group_size;
+                    const unsigned long long diag = (tiles - 1) * p.group_size * p.group_size + last * last;
+                    p.evals[h] += nn * hd.n_ext + (nn * nn + diag) / 2;
+                } else {
+                    p.evals[h] += nn * static_cast<unsigned long long>(n_old + hd.n_ext);
+                }
                 const int changed = n_new != n_old;
                 p.converged[h] = (!changed || n_new == 0) ? 1 : 0;
                 act = (changed && n_new > 0 && it < p.max_iter) ? 1 : 0;

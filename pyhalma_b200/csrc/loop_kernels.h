@@ -28,6 +28,7 @@ struct LoopParams {
     int32_t *cnt, *cnt_next, *iter, *active, *active_next, *halo_buf, *nsplit, *item_base, *converged;
     double *hM, *hvb, *hvb_next, *hcom;
     unsigned long long *pairs;
+    unsigned long long *evals;            // per halo: 1/r evaluations actually made (< pairs in symmetric mode)
     // per-chunk scratch
     int32_t *chunk_cnt, *chunk_off;
     double *chunk_sum;                    // kChunkSums per chunk: m, m*v[3], m*x[3] of the survivors,

@@ -887,9 +887,21 @@ const FastVariant kVariants[] = {
 #undef HALMA_VARIANT
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-// The kernel that also runs the symmetric tickets: the throughput shape with room for the extra
-// registers of the two-sided body (128 per thread, 4 blocks per SM).
-const auto kSymKernel = k_potential_fast<4, 4, true, true>;
+// The kernel that also runs the symmetric tickets.  6 resident blocks per SM (80 registers, a few
+// spill slots outside the hot loop) beat 5 and 4 by 2-5 % (profiles/np_variants_r01.txt).
+typedef void (*SymKernel)(const PotParams);
+const SymKernel kSymKernels[3] = {k_potential_fast<4, 4, true, true>, k_potential_fast<4, 5, true, true>,
+                                  k_potential_fast<4, 6, true, true>};
+int sym_choice()
+{
+    static int c = [] {
+        const char *e = getenv("HALMA_SYM_MINB");       // tuning: 4, 5 or 6 resident blocks per SM
+        const int v = e ? atoi(e) : 6;
+        return v >= 4 && v <= 6 ? v - 4 : 0;
+    }();
+    return c;
+}
+#define kSymKernel kSymKernels[sym_choice()]
 int g_bps[16] = {0};
 int g_sym_bps = 0;
 

@@ -37,7 +37,8 @@ class RunStats:
     potential_launches: int
     launches: int
     passes: int
-    pairs: int
+    pairs: int                        # (target, source) interactions: what the reference's loop visits
+    evaluations: int = 0              # 1/r evaluations made for them (fewer than pairs in symmetric mode)
 
 
 @dataclass
@@ -227,7 +228,8 @@ class UnbindPlan:
         st = _lib.RunStats()
         _lib.check(self._L.halma_plan_run(self._h, C.byref(st)))
         self._keep = []
-        return RunStats(st.total_ms, st.potential_ms, st.potential_launches, st.launches, st.passes, st.pairs)
+        return RunStats(st.total_ms, st.potential_ms, st.potential_launches, st.launches, st.passes, st.pairs,
+                        st.evaluations)
 
     def download(self, mask=True, be=True, energy=True, idx=True, halos=True) -> CatalogueResult:
         n = self.n

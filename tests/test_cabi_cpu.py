@@ -30,7 +30,7 @@ def test_header_symbols_are_exported():
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.UnbindConfig) == 64
     assert ctypes.sizeof(_lib.HaloResult) == 120
-    assert ctypes.sizeof(_lib.RunStats) == 40
+    assert ctypes.sizeof(_lib.RunStats) == 48
 
 
 def test_abi_version():
