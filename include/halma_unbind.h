@@ -130,12 +130,14 @@ typedef struct halma_unbind_config {
                                 enqueues passes ahead of the device and learns about convergence from
                                 a pinned flag; gives per-launch CUDA-event timing in halma_run_stats.
                                 Ignored (0) in split mode.                                   */
-    int32_t symmetric;       /* 1 (FAST mode, one GPU, use_graph = 0, plans large enough for the predicate-
-                                free kernel): every member x member pair of different 128-member tiles is
+    int32_t symmetric;       /* 1 (FAST mode, plans large enough for the predicate-free kernel's throughput
+                                shape): every member x member pair of different 128-member tiles is
                                 evaluated once and feeds both particles' sums -- half the rsqrt work of the
-                                self term.  The two-sided sums are accumulated with float64 atomics, so
-                                results are reproducible to ~1e-16 of the potential rather than bit for
-                                bit; everything else (predicate, tolerances, outputs) is unchanged.    */
+                                self term.  The two-sided sums are float64 atomics of addends rounded to a
+                                per-halo quantum (2^-42 of M/extent) inside whose window the additions
+                                are exact, so runs stay bit-reproducible; a halo whose sums leave the
+                                window (potential > ~1000 M/extent) is recomputed one-sided.  Predicate,
+                                tolerances and outputs are unchanged.                                  */
 } halma_unbind_config;
 
 typedef struct halma_halo_result {

@@ -473,7 +473,7 @@ struct halma_plan {
     DBuf<int32_t> d_hint;                 // per-halo int arrays: 9 * n_halo + (n_halo + 1)
     DBuf<double> d_hdbl;                  // per-halo doubles: M(1) vb(3) vb_next(3) com(3)
     DBuf<unsigned long long> d_pairs, d_evals;
-    DBuf<double> d_phi_sym;
+    DBuf<double> d_phi_sym, d_symq;
     bool sym = false;
     DBuf<int32_t> d_cint;                 // per-chunk ints: cnt, off
     DBuf<double> d_csum;                  // kChunkSums per chunk
@@ -519,7 +519,7 @@ struct halma_plan {
         d_halo.release(); d_chunk_halo.release(); d_chunk_p0.release(); d_order.release();
         d_ext_off.clear();
         d_in.release(); d_ext.release(); d_stage.release(); d_vb_user.release(); d_work.release();
-        d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_evals.release(); d_cint.release(); d_phi_sym.release();
+        d_widx.release(); d_hint.release(); d_hdbl.release(); d_pairs.release(); d_evals.release(); d_cint.release(); d_phi_sym.release(); d_symq.release();
         d_csum.release(); d_flag.release(); d_mask.release(); d_be.release(); d_E.release();
         d_idx.release(); d_phi.release(); d_st.release();
         d_cbest.release(); d_cbestq.release(); d_hbest.release(); d_hrps.release(); d_temp.release();
@@ -810,13 +810,16 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
         const SortedAxisMut &A = P->sax[a];
         L.ax[a] = SortedAxis{A.x, A.y, A.z, A.m, A.key, A.slot, A.tgt, A.inv, A.corr};
     }
-    // symmetric self-term: rides on the predicate-free kernel's throughput shape (128-member tiles),
-    // one GPU, host-enqueued loop (the per-pass memset of phi_sym is not part of the graph body)
-    P->sym = cfg.symmetric && P->np && cfg.n_ranks == 1 && !cfg.use_graph && P->variant == 0 &&
-             potential_group_size(cfg.mode, P->variant) == 128;
-    if (P->sym) CU_TRY(P->d_phi_sym.alloc(NP));
+    // symmetric self-term: rides on the predicate-free kernel's throughput shape (128-member tiles)
+    P->sym = cfg.symmetric && P->np && P->variant == 0 && potential_group_size(cfg.mode, P->variant) == 128;
+    if (P->sym) {
+        CU_TRY(P->d_phi_sym.alloc(NP));
+        CU_TRY(P->d_symq.alloc(2 * nh));
+    }
     L.phi_sym = P->d_phi_sym.p;
     L.sym_enabled = P->sym ? 1 : 0;
+    L.sym_ext = P->d_symq.p;
+    L.sym_q = P->sym ? P->d_symq.p + nh : nullptr;
 
     PotParams &Q = P->pp;
     memset(&Q, 0, sizeof Q);
@@ -844,6 +847,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     Q.np_enabled = P->np ? 1 : 0;
     Q.redo_only = 0;
     Q.phi_sym = P->d_phi_sym.p;
+    Q.sym_q = L.sym_q;
     Q.sym_enabled = P->sym ? 1 : 0;
     for (int a = 0; a < 3 && P->np; ++a) {
         Q.ax[a] = L.ax[a];
@@ -1067,6 +1071,7 @@ static int enqueue_pass_kernels(halma_plan *P, const LoopParams &lp)
     cudaStream_t s = P->stream;
     const int sm = P->ctx->sm_count;
     const int grid = sm * P->ctx->blocks(P->cfg.mode, P->variant);
+    if (P->sym) CU_TRY(cudaMemsetAsync(P->d_phi_sym.p, 0, static_cast<size_t>(P->n_pad) * sizeof(double), s));
     CU_TRY(potential_launch(P->pp, P->cfg.mode, P->variant, grid, s));
     if (P->np) {
         PotParams redo = P->pp;
@@ -1149,6 +1154,13 @@ static int enqueue_pass(halma_plan *P, int pass)
         int e = g_nccl.AllReduce(P->d_phi.p, P->d_phi.p, static_cast<size_t>(P->n_pad), /*ncclFloat64*/ 8,
                                  /*ncclSum*/ 0, P->comm, s);
         if (e) return nccl_fail(e, "ncclAllReduce");
+        if (P->sym) {
+            // every rank summed the two-sided terms of its row tiles; the addends are multiples of the
+            // halo's quantum and the totals stay inside the exact window, so this sum is exact too
+            e = g_nccl.AllReduce(P->d_phi_sym.p, P->d_phi_sym.p, static_cast<size_t>(P->n_pad), /*ncclFloat64*/ 8,
+                                 /*ncclSum*/ 0, P->comm, s);
+            if (e) return nccl_fail(e, "ncclAllReduce(symmetric sums)");
+        }
         CU_TRY(launch_set_nsplit_one(P->lp, s));
     }
     CU_TRY(launch_energy_flag(P->lp, sm, s));
@@ -1186,6 +1198,7 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         CU_TRY(cudaMemcpyAsync(P->lp.hvb, P->d_vb_user.p, 3 * nh * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if (nh > 0) {
         CU_TRY(launch_pack_members(P->lp, sm, s));
+        if (P->sym) CU_TRY(launch_halo_extent(P->lp, s));
         if (int rc = plan_prepare_sorted(P)) return rc;
         CU_TRY(launch_halo_decide(P->lp, 1, sm, s));
         CU_TRY(launch_schedule(P->lp, 1, s));

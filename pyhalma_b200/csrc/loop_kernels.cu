@@ -123,6 +123,51 @@ __global__ void __launch_bounds__(kCh) k_pack_members(const LoopParams p)
     }
 }
 
+// Symmetric mode: largest coordinate extent of every halo's members (float32 working set, right
+// after the pack).  With the bound mass it sets the quantum that makes the two-sided sums exact.
+__global__ void __launch_bounds__(kCh) k_halo_extent(const LoopParams p)
+{
+    __shared__ float smn[3][kCh / 32], smx[3][kCh / 32];
+    for (int h = blockIdx.x; h < p.n_halo; h += gridDim.x) {
+        const HaloDesc &hd = p.halo[h];
+        const float inf = __int_as_float(0x7f800000);
+        float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+        for (int q = threadIdx.x; q < hd.n0; q += kCh) {
+            const float v[3] = {p.wx[0][hd.poff + q], p.wy[0][hd.poff + q], p.wz[0][hd.poff + q]};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = fminf(mn[a], v[a]);
+                mx[a] = fmaxf(mx[a], v[a]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[a] = fminf(mn[a], __shfl_down_sync(0xffffffffu, mn[a], o));
+                mx[a] = fmaxf(mx[a], __shfl_down_sync(0xffffffffu, mx[a], o));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                smn[a][threadIdx.x >> 5] = mn[a];
+                smx[a][threadIdx.x >> 5] = mx[a];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ext = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                float lo = smn[a][0], hi = smx[a][0];
+                for (int w = 1; w < kCh / 32; ++w) {
+                    lo = fminf(lo, smn[a][w]);
+                    hi = fmaxf(hi, smx[a][w]);
+                }
+                ext = fmax(ext, static_cast<double>(hi) - static_cast<double>(lo));
+            }
+            p.sym_ext[h] = ext;          // NaN coordinates are skipped by fmin/fmax; an empty halo gives -inf -> 0 below
+        }
+        __syncthreads();
+    }
+}
+
 // One external group: user CSR layout (float64) -> padded float32 segment of each halo.
 __global__ void __launch_bounds__(256) k_pack_group(const HaloDesc *halo, int n_halo, int seg_index,
                                                     const int64_t *ext_off, const double *m, const double *x,
@@ -322,6 +367,20 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
                 p.hbest[h] = best_q;
             }
             p.hM[h] = M;
+            if (p.sym_enabled) {
+                // Quantum of the symmetric sums of the coming pass: every addend is rounded to a multiple of
+                // q = 2^-42 * 2^ceil(log2(M / extent)), and a sum that stays below 2^52 q = 1024 * (1..2) * M / extent
+                // is then EXACT in float64, so the order of the atomics cannot change it.  A sum that leaves the
+                // window sends the halo to the one-sided kernel (potential.cu::sym_ticket).  0 = no quantisation.
+                const double ext = p.sym_ext[h];
+                double q = 0.0;
+                if (M > 0.0 && ext > 0.0 && M <= 1.7976931348623157e308 && ext <= 1.7976931348623157e308) {
+                    int e;
+                    frexp(M / ext, &e);                   // M / ext = f * 2^e, 0.5 <= f < 1
+                    if (e > -900 && e < 900) q = ldexp(1.0, e - 42);
+                }
+                p.sym_q[h] = q;
+            }
             const double inv = M > 0.0 ? 1.0 / M : 0.0;
             // halo_properties.py:39-43, 56-60: sums divided by M, zeros when M == 0
             for (int k = 0; k < 3; ++k) {
@@ -619,6 +678,13 @@ cudaError_t launch_pack_group(const HaloDesc *halo, int n_halo, int seg_index, i
 cudaError_t launch_energy_flag(const LoopParams &p, int sm_count, cudaStream_t s)
 {
     k_energy_flag<<<chunk_grid(p, sm_count), kCh, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_extent(const LoopParams &p, cudaStream_t s)
+{
+    const int g = p.n_halo < 4096 ? (p.n_halo > 0 ? p.n_halo : 1) : 4096;
+    k_halo_extent<<<g, kCh, 0, s>>>(p);
     return cudaGetLastError();
 }
 

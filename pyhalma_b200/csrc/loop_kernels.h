@@ -56,11 +56,14 @@ struct LoopParams {
     // symmetric self-term (potential.cu::sym_ticket): off-diagonal member x member sums
     const double *phi_sym;                // [n_pad]
     int32_t sym_enabled;
+    double *sym_ext;                      // [n_halo] largest coordinate extent of the halo's members
+    double *sym_q;                        // [n_halo] quantum of the symmetric sums for the coming pass
     // CUDA-graph loop driver: conditional handle of the WHILE node (0 = not in a graph)
     unsigned long long cond_handle;
 };
 
 cudaError_t launch_pack_members(const LoopParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_halo_extent(const LoopParams &p, cudaStream_t s);
 cudaError_t launch_pack_group(const HaloDesc *halo, int n_halo, int seg_index, int max_count,
                               const int64_t *ext_off, const double *m, const double *x, const double *y,
                               const double *z, float *em, float *ex, float *ey, float *ez, cudaStream_t s);

@@ -222,7 +222,7 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
     t.corr_axis = 3;
     t.group = local / chunks;
     t.s = local % chunks;
-    return true;
+    return t.group % p.n_ranks == p.rank;      // split mode: row tiles are dealt round-robin like the target groups
 }
 
 // ---------------------------------------------------------------------------------------
@@ -441,8 +441,8 @@ __device__ __forceinline__ void correction_ticket(const PotParams &p, const Tick
 // tiles J > I through the TMA ring.  Inside a tile lanes sweep the 64 source PAIRS in rotation
 // (lane l visits pair (k + l) mod 64 at step k), so the column partial sums live in shared memory
 // as plain read-modify-writes without conflicts.  Row and column sums are added to phi_sym with
-// float64 atomics: their order is not fixed, so a symmetric run is reproducible to ~1e-16 of the
-// potential (before its float32 rounding), not bit for bit -- which is why the mode is opt-in.
+// float64 atomics whose order is not fixed; the addends are therefore rounded to a per-halo quantum
+// inside whose window float64 addition is exact (sym_add), which keeps runs bit-reproducible.
 // scripts/probes/symmetric_probe.cu: 3.4-3.5 T pair evaluations/s = 6.8-7.1 T interactions/s.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void sym_tile(const float *__restrict__ stage, float *__restrict__ col, const float (&xi)[4],
@@ -489,6 +489,19 @@ __device__ __forceinline__ void sym_tile(const float *__restrict__ stage, float 
     }
 }
 
+// Adds v, rounded to a multiple of q, to *dst; returns true when the sum left the window in which
+// float64 addition of such multiples is exact (the caller then hands the halo to the one-sided kernel).
+__device__ __forceinline__ bool sym_add(double *dst, double v, double q, double inv_q, double window)
+{
+    if (q > 0.0) {
+        v = __dmul_rn(rint(__dmul_rn(v, inv_q)), q);
+        const double old = atomicAdd(dst, v);
+        return !(fabs(old + v) < window);
+    }
+    atomicAdd(dst, v);
+    return false;
+}
+
 __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk, Ring &rg, float *col, int lane,
                                            int parity)
 {
@@ -513,6 +526,10 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
         acc64[t] = 0.0;
     }
     bool bad = false;
+    // addends are rounded to multiples of q; while every running sum stays inside +-2^52 q the float64
+    // additions are exact and their order does not matter (loop_kernels.cu::k_halo_decide)
+    // (split mode: every rank keeps to its share of the window, so the all-reduced total fits too)
+    const double q = p.sym_q[tk.h], inv_q = q > 0.0 ? 1.0 / q : 0.0, window = ldexp(q, 52) / p.n_ranks;
     TileCursor prod;
     prod.init_range(parity, base + static_cast<int64_t>(j0) * kTileJ, min(n, j1 * kTileJ) - j0 * kTileJ);
     TileCursor cons = prod;
@@ -553,9 +570,9 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
 #pragma unroll
         for (int e = lane; e < kTileJ; e += 32)
             if (e < len) {
-                const float v = col[e];
-                bad |= !(fabsf(v) <= 3.4028234e38f);
-                atomicAdd(&p.phi_sym[tile0 + e], static_cast<double>(v));
+                const float vf = col[e];
+                bad |= !(fabsf(vf) <= 3.4028234e38f);
+                bad |= sym_add(&p.phi_sym[tile0 + e], static_cast<double>(vf), q, inv_q, window);
             }
         __syncwarp();      // every lane is done with this stage and with col before they are reused
         rg.use = (rg.use + 1 == kStages) ? 0 : rg.use + 1;
@@ -564,7 +581,7 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         bad |= !(fabs(acc64[t]) <= 1.7976931348623157e308);
-        atomicAdd(&p.phi_sym[base + I * kTileJ + t * 32 + lane], acc64[t]);
+        bad |= sym_add(&p.phi_sym[base + I * kTileJ + t * 32 + lane], acc64[t], q, inv_q, window);
     }
     // a zero separation between different tiles (exact duplicates) or non-finite input: the
     // predicated kernel recomputes the halo from scratch and phi_sym is ignored for it

@@ -138,7 +138,7 @@ class UnbindPlan:
         cfg.use_graph = int(bool(use_graph))
         if symmetric is None:
             import os
-            symmetric = os.environ.get("HALMA_SYMMETRIC", "0") not in ("0", "")
+            symmetric = os.environ.get("HALMA_SYMMETRIC", "1") not in ("0", "")      # on unless HALMA_SYMMETRIC=0
         cfg.symmetric = int(bool(symmetric))
         self.cfg = cfg
         ptrs = (C.POINTER(C.c_int64) * max(1, len(self.ext_offsets)))()

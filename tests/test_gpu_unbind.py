@@ -534,7 +534,8 @@ def test_predicate_free_path_forced_on_small_and_odd_inputs():
 
 
 def test_symmetric_self_term_against_one_sided_and_oracle():
-    """halma_unbind_config.symmetric: member x member pairs of different tiles are evaluated once for
+    """halma_unbind_config.symmetric (on by default in the Python layer; HALMA_SYMMETRIC=0 turns it
+    off): member x member pairs of different tiles are evaluated once for
     both particles.  Same predicate, same per-pair arithmetic; only the order of the float64 partial
     sums differs, so potentials agree with the one-sided kernel and with the float64 oracle within
     the FAST tolerance (1e-6) and masks outside the 1e-6 energy band."""
@@ -546,8 +547,9 @@ def test_symmetric_self_term_against_one_sided_and_oracle():
     dm = synth.dm_cloud(3000, 20 * synth.KPC, 1e7, rng)
     kw = dict(pre=[gas.pos_mass()], post=[dm.pos_mass()], kappa=9.0)
     args = (st.x, st.y, st.z, st.vx, st.vy, st.vz, st.mass)
-    one = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, **kw)
+    one = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=False, **kw)
     sym = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=True, **kw)
+    assert sym.stats.evaluations < 0.56 * one.stats.evaluations and one.stats.evaluations == one.stats.pairs
     ref = O.unbind_halo(*args, variant="f64acc", max_iter=1, vb_fixed=synth.BULK_V, **kw)
     np.testing.assert_allclose(sym.be32, ref.be32, rtol=1e-6)
     np.testing.assert_allclose(sym.be32, one.be32, rtol=1e-6)
@@ -555,8 +557,13 @@ def test_symmetric_self_term_against_one_sided_and_oracle():
     diff = sym.mask != ref.mask
     assert np.all(O.energy_margin(ref.energy, ref.be32, 9.0)[diff] < 1e-6)
     assert sym.pairs == one.pairs                  # interactions are counted the same way
+    # the two-sided sums are rounded to a per-halo quantum inside whose window float64 addition is
+    # exact, so the order of the atomics cannot show: a second run is bit-identical
+    again = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=True, **kw)
+    assert np.array_equal(again.be32.view(np.uint32), sym.be32.view(np.uint32))
+    assert np.array_equal(again.energy, sym.energy) and np.array_equal(again.mask, sym.mask)
     # iterated to the fixed point: same member set as the one-sided run (up to the energy band)
-    one = unbind_halo(*args, mode="fast", **kw)
+    one = unbind_halo(*args, mode="fast", symmetric=False, **kw)
     sym = unbind_halo(*args, mode="fast", symmetric=True, **kw)
     assert sym.n_iter == one.n_iter and np.count_nonzero(sym.mask != one.mask) <= 2
     np.testing.assert_allclose(sym.mass, one.mass, rtol=1e-4)
@@ -565,7 +572,7 @@ def test_symmetric_self_term_against_one_sided_and_oracle():
     x2 = st.x.copy(); y2 = st.y.copy(); z2 = st.z.copy()
     x2[60_000], y2[60_000], z2[60_000] = x2[17], y2[17], z2[17]
     a2 = (x2, y2, z2, st.vx, st.vy, st.vz, st.mass)
-    one = unbind_halo(*a2, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, **kw)
+    one = unbind_halo(*a2, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=False, **kw)
     sym = unbind_halo(*a2, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=True, **kw)
     assert np.all(np.isfinite(sym.be32))
     np.testing.assert_array_equal(sym.be32, one.be32)          # both took the same fallback
@@ -582,7 +589,7 @@ def test_symmetric_mode_forced_on_small_and_odd_inputs():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, HALMA_NP_MIN_PAIRS="0", HALMA_SYMMETRIC="1", HALMA_FAST_VARIANT="0")
     sel = ("ragged or degenerate or duplicates or zero_mass or external_groups or golden_fast or fused_large "
-           "or fast_mode_against or lattice or rps_mass_sums or cfg3_full or cfg2_full")
+           "or fast_mode_against or lattice or rps_mass_sums or cfg3_full or cfg2_full or idempotence or graph_loop")
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_unbind.py"), "-q", "-x",
                           "-m", "gpu", "-k", sel], capture_output=True, text=True, timeout=1500, env=env, cwd=root)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
