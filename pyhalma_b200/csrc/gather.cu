@@ -413,6 +413,22 @@ struct halma_snapshot {
 
 namespace {
 
+// Stream-ordered scratch that is returned to the pool on every exit path.
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    explicit Scratch(cudaStream_t stream) : s(stream) {}
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+    template <class T>
+    T *as() const { return static_cast<T *>(p); }
+    ~Scratch()
+    {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+
 int ensure_scan_tmp(halma_snapshot *s, int64_t n)
 {
     size_t need = 0;
@@ -505,13 +521,13 @@ int build_index(halma_snapshot *s, int kind)
     const double *x = s->d_part[kind], *y = x + nn, *z = x + 2 * nn;
     // bounding box
     const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(s->sm) * 8));
-    double *d_mm = nullptr;
-    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_mm), blocks * 6 * sizeof(double), s->stream));
+    Scratch mm_buf(s->stream);
+    GA_TRY(mm_buf.alloc(blocks * 6 * sizeof(double)));
+    double *d_mm = mm_buf.as<double>();
     k_minmax<<<blocks, 256, 0, s->stream>>>(x, y, z, n, d_mm);
     GA_TRY(cudaGetLastError());
     std::vector<double> mm(static_cast<size_t>(blocks) * 6);
     GA_TRY(cudaMemcpyAsync(mm.data(), d_mm, mm.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    GA_TRY(cudaFreeAsync(d_mm, s->stream));
     GA_TRY(cudaStreamSynchronize(s->stream));
     double lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
@@ -532,12 +548,12 @@ int build_index(halma_snapshot *s, int kind)
         g.inv_h[a] = ext > 0 && std::isfinite(g.G / ext) ? g.G / ext : 0.0;
     }
     const int64_t n_cells = static_cast<int64_t>(g.G) * g.G * g.G;
-    uint32_t *d_key = nullptr, *d_key2 = nullptr;
-    int32_t *d_idx = nullptr;
-    void *d_tmp = nullptr;
-    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_key), nn * sizeof(uint32_t), s->stream));
-    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_key2), nn * sizeof(uint32_t), s->stream));
-    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_idx), nn * sizeof(int32_t), s->stream));
+    Scratch key_buf(s->stream), key2_buf(s->stream), idx_buf(s->stream), tmp_buf(s->stream);
+    GA_TRY(key_buf.alloc(nn * sizeof(uint32_t)));
+    GA_TRY(key2_buf.alloc(nn * sizeof(uint32_t)));
+    GA_TRY(idx_buf.alloc(nn * sizeof(int32_t)));
+    uint32_t *d_key = key_buf.as<uint32_t>(), *d_key2 = key2_buf.as<uint32_t>();
+    int32_t *d_idx = idx_buf.as<int32_t>();
     GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_perm[kind]), nn * sizeof(int32_t), s->stream));
     GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&s->d_cell_start[kind]), (n_cells + 1) * sizeof(int32_t), s->stream));
     k_cell_keys<<<blocks, 256, 0, s->stream>>>(x, y, z, n, g, d_key, d_idx);
@@ -547,16 +563,12 @@ int build_index(halma_snapshot *s, int kind)
     size_t tmp_bytes = 0;
     GA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_idx, s->d_perm[kind], static_cast<int>(n), 0,
                                            bits, s->stream));
-    GA_TRY(cudaMallocAsync(&d_tmp, tmp_bytes, s->stream));
-    GA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_idx, s->d_perm[kind], static_cast<int>(n), 0,
+    GA_TRY(tmp_buf.alloc(tmp_bytes));
+    GA_TRY(cub::DeviceRadixSort::SortPairs(tmp_buf.p, tmp_bytes, d_key, d_key2, d_idx, s->d_perm[kind], static_cast<int>(n), 0,
                                            bits, s->stream));
     const int cb = static_cast<int>(std::min<int64_t>((n_cells + 256) / 256, static_cast<int64_t>(s->sm) * 16));
     k_cell_start<<<cb, 256, 0, s->stream>>>(d_key2, n, n_cells, s->d_cell_start[kind]);
     GA_TRY(cudaGetLastError());
-    GA_TRY(cudaFreeAsync(d_tmp, s->stream));
-    GA_TRY(cudaFreeAsync(d_key, s->stream));
-    GA_TRY(cudaFreeAsync(d_key2, s->stream));
-    GA_TRY(cudaFreeAsync(d_idx, s->stream));
     GA_TRY(cudaStreamSynchronize(s->stream));
     s->geom[kind] = g;
     s->indexed[kind] = true;
@@ -589,8 +601,9 @@ int run_indexed_ball(halma_snapshot *s, int kind, BallSel &bs, int64_t *total, A
     r.iz0 = lo[2]; r.nz = hi[2] - lo[2] + 1;
     r.G = g.G;
     const int64_t rows = static_cast<int64_t>(r.ny) * r.nz;
-    int64_t *d_len = nullptr;
-    GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_len), 2 * (rows + 1) * sizeof(int64_t), s->stream));
+    Scratch len_buf(s->stream), sel_buf(s->stream), sort_buf(s->stream);
+    GA_TRY(len_buf.alloc(2 * (rows + 1) * sizeof(int64_t)));
+    int64_t *d_len = len_buf.as<int64_t>();
     int64_t *d_off = d_len + rows + 1;
     k_row_len<<<static_cast<int>((rows + 256) / 256), 256, 0, s->stream>>>(s->d_cell_start[kind], r, d_len);
     GA_TRY(cudaGetLastError());
@@ -601,10 +614,7 @@ int run_indexed_ball(halma_snapshot *s, int kind, BallSel &bs, int64_t *total, A
     GA_TRY(cudaMemcpyAsync(&n_cand, d_off + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
     GA_TRY(cudaStreamSynchronize(s->stream));
     // a query that covers a large part of the particles is cheaper as one streaming pass
-    if (n_cand * 3 > s->n_part[kind]) {
-        GA_TRY(cudaFreeAsync(d_len, s->stream));
-        return run_selection(s, bs, s->n_part[kind], total, alloc_outputs);
-    }
+    if (n_cand * 3 > s->n_part[kind]) return run_selection(s, bs, s->n_part[kind], total, alloc_outputs);
     IndexedBallSel is;
     is.b = bs;
     is.perm = s->d_perm[kind];
@@ -615,7 +625,8 @@ int run_indexed_ball(halma_snapshot *s, int kind, BallSel &bs, int64_t *total, A
     int32_t *d_sel = nullptr, *d_sorted = nullptr;
     int rc = run_selection(s, is, n_cand, total, [&](IndexedBallSel &sel, int64_t k) -> int {
         if (k > 0) {
-            GA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_sel), 2 * k * sizeof(int32_t), s->stream));
+            GA_TRY(sel_buf.alloc(2 * k * sizeof(int32_t)));
+            d_sel = sel_buf.as<int32_t>();
             d_sorted = d_sel + k;
             sel.out_idx = d_sel;
         }
@@ -626,22 +637,18 @@ int run_indexed_ball(halma_snapshot *s, int kind, BallSel &bs, int64_t *total, A
     if (int rc2 = alloc_outputs(bs, k)) return rc2;
     if (k > 0) {
         if (k >= INT32_MAX) return halma_internal_fail(HALMA_ERR_TOO_LARGE, "selection too large");
-        void *d_tmp = nullptr;
         size_t tb = 0;
         int bits = 1;
         while ((int64_t(1) << bits) < s->n_part[kind]) ++bits;
         const uint32_t *kin = reinterpret_cast<const uint32_t *>(d_sel);
         uint32_t *kout = reinterpret_cast<uint32_t *>(d_sorted);
         GA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb, kin, kout, static_cast<int>(k), 0, bits, s->stream));
-        GA_TRY(cudaMallocAsync(&d_tmp, tb, s->stream));
-        GA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, tb, kin, kout, static_cast<int>(k), 0, bits, s->stream));
+        GA_TRY(sort_buf.alloc(tb));
+        GA_TRY(cub::DeviceRadixSort::SortKeys(sort_buf.p, tb, kin, kout, static_cast<int>(k), 0, bits, s->stream));
         const int eb = static_cast<int>(std::min<int64_t>((k + 255) / 256, static_cast<int64_t>(s->sm) * 16));
         k_emit_rows<<<eb, 256, 0, s->stream>>>(bs, d_sorted, k);
         GA_TRY(cudaGetLastError());
-        GA_TRY(cudaFreeAsync(d_tmp, s->stream));
-        GA_TRY(cudaFreeAsync(d_sel, s->stream));
     }
-    GA_TRY(cudaFreeAsync(d_len, s->stream));
     return HALMA_OK;
 }
 
