@@ -57,6 +57,50 @@ class HaloResult:
     unbound_hot_mass: float = 0.0
 
 
+class HaloResults:
+    """Sequence of HaloResult over the array halma_plan_download filled; the Python objects are
+    made on access (a catalogue has 1e4 haloes and most callers look at a few fields of a few)."""
+
+    def __init__(self, raw, n):
+        self._raw = raw
+        self._n = n
+
+    def __len__(self):
+        return self._n
+
+    def _make(self, h):
+        r = self._raw[h]
+        return HaloResult(int(r.n_bound), int(r.n_iter), bool(r.converged), float(r.mass), tuple(r.com), tuple(r.vb),
+                          int(r.pairs), int(r.most_bound), float(r.mass_initial), float(r.cold_bound_mass),
+                          float(r.unbound_cold_mass), float(r.unbound_hot_mass))
+
+    def __getitem__(self, h):
+        if isinstance(h, slice):
+            return [self._make(k) for k in range(*h.indices(self._n))]
+        if h < 0:
+            h += self._n
+        if not 0 <= h < self._n:
+            raise IndexError(h)
+        return self._make(h)
+
+    def __iter__(self):
+        return (self._make(h) for h in range(self._n))
+
+    def field(self, name) -> np.ndarray:
+        """One field of every halo as an array (n_bound, n_iter, converged, mass, pairs, most_bound,
+        mass_initial, cold_bound_mass, unbound_cold_mass, unbound_hot_mass: shape (n,); com, vb: (n, 3))."""
+        if self._n == 0:
+            return np.zeros((0, 3) if name in ("com", "vb") else 0)
+        a = np.frombuffer(self._raw, dtype=_HALO_DTYPE, count=self._n)
+        return a[name].copy()
+
+
+_HALO_DTYPE = np.dtype([("n_bound", np.int64), ("n_iter", np.int32), ("converged", np.int32), ("mass", np.float64),
+                        ("com", np.float64, 3), ("vb", np.float64, 3), ("pairs", np.int64), ("most_bound", np.int64),
+                        ("mass_initial", np.float64), ("cold_bound_mass", np.float64),
+                        ("unbound_cold_mass", np.float64), ("unbound_hot_mass", np.float64)])
+
+
 @dataclass
 class CatalogueResult:
     offsets: np.ndarray
@@ -64,7 +108,7 @@ class CatalogueResult:
     be32: Optional[np.ndarray]
     energy: Optional[np.ndarray]
     idx_packed: Optional[np.ndarray]
-    halos: List[HaloResult]
+    halos: Sequence[HaloResult]
     stats: Optional[RunStats] = None
 
     def members(self, h: int) -> np.ndarray:
@@ -242,14 +286,7 @@ class UnbindPlan:
         _lib.check(self._L.halma_plan_download(
             self._h, m.ctypes.data if mask else None, b.ctypes.data if be else None,
             e.ctypes.data if energy else None, i.ctypes.data if idx else None, hr))
-        out = []
-        if halos:
-            for h in range(self.n_halo):
-                r = hr[h]
-                out.append(HaloResult(int(r.n_bound), int(r.n_iter), bool(r.converged), float(r.mass),
-                                      tuple(r.com), tuple(r.vb), int(r.pairs), int(r.most_bound),
-                                      float(r.mass_initial), float(r.cold_bound_mass),
-                                      float(r.unbound_cold_mass), float(r.unbound_hot_mass)))
+        out = HaloResults(hr, self.n_halo) if halos else []
         return CatalogueResult(self.offsets, m, b, e, i, out)
 
 

@@ -81,3 +81,21 @@ def test_wrapper_empty_targets_needs_no_gpu():
     from pyhalma_b200 import halo_gas
     out = halo_gas.brute_force_binding_energy_fortran(np.ones(3), np.ones(3), np.ones(3), np.ones(3), [], [], [])
     assert out.shape == (0,) and out.dtype == np.float64        # halo_gas.py:169-170
+
+
+def test_halo_results_view_matches_struct_layout():
+    """unbind.HaloResults reads halma_halo_result records in place: its numpy dtype must mirror the
+    ctypes structure (and through test_struct_sizes_match_header the C header)."""
+    from pyhalma_b200.unbind import _HALO_DTYPE, HaloResults
+    assert _HALO_DTYPE.itemsize == ctypes.sizeof(_lib.HaloResult)
+    for (name, _t), f in zip(_lib.HaloResult._fields_, _HALO_DTYPE.names):
+        assert name == f and getattr(_lib.HaloResult, name).offset == _HALO_DTYPE.fields[f][1], name
+    hr = (_lib.HaloResult * 3)()
+    hr[1].n_bound, hr[1].mass, hr[1].most_bound = 7, 2.5, 4
+    hr[1].com[2] = 9.0
+    r = HaloResults(hr, 3)
+    assert len(r) == 3 and r[1].n_bound == 7 and r[-2].mass == 2.5 and r[1].com == (0.0, 0.0, 9.0)
+    assert [h.most_bound for h in r] == [0, 4, 0] and len(r[0:2]) == 2
+    assert list(r.field("n_bound")) == [0, 7, 0] and r.field("com").shape == (3, 3)
+    with pytest.raises(IndexError):
+        r[3]
