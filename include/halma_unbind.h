@@ -134,9 +134,9 @@ typedef struct halma_unbind_config {
                                 shape): every member x member pair of different 128-member tiles is
                                 evaluated once and feeds both particles' sums -- half the rsqrt work of the
                                 self term.  The two-sided sums are float64 atomics of addends rounded to a
-                                per-halo quantum (2^-42 of M/extent) inside whose window the additions
+                                per-halo quantum (2^-37 of M/extent) inside whose window the additions
                                 are exact, so runs stay bit-reproducible; a halo whose sums leave the
-                                window (potential > ~1000 M/extent) is recomputed one-sided.  Predicate,
+                                window (potential > ~3e4 M/extent) is recomputed one-sided.  Predicate,
                                 tolerances and outputs are unchanged.                                  */
 } halma_unbind_config;
 

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
             p.hM[h] = M;
             if (p.sym_enabled) {
                 // Quantum of the symmetric sums of the coming pass: every addend is rounded to a multiple of
-                // q = 2^-42 * 2^ceil(log2(M / extent)), and a sum that stays below 2^52 q = 1024 * (1..2) * M / extent
+                // q = 2^-37 * 2^ceil(log2(M / extent)), and a sum that stays below 2^52 q = 32768 * (1..2) * M / extent
                 // is then EXACT in float64, so the order of the atomics cannot change it.  A sum that leaves the
                 // window sends the halo to the one-sided kernel (potential.cu::sym_ticket).  0 = no quantisation.
                 const double ext = p.sym_ext[h];
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
                 if (M > 0.0 && ext > 0.0 && M <= 1.7976931348623157e308 && ext <= 1.7976931348623157e308) {
                     int e;
                     frexp(M / ext, &e);                   // M / ext = f * 2^e, 0.5 <= f < 1
-                    if (e > -900 && e < 900) q = ldexp(1.0, e - 42);
+                    if (e > -900 && e < 900) q = ldexp(1.0, e - 37);
                 }
                 p.sym_q[h] = q;
             }

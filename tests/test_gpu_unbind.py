@@ -594,3 +594,25 @@ def test_symmetric_mode_forced_on_small_and_odd_inputs():
                           "-m", "gpu", "-k", sel], capture_output=True, text=True, timeout=1500, env=env, cwd=root)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout
+
+
+def test_symmetric_exact_window_with_far_outliers():
+    """The two-sided sums are exact inside +-2^52 q ~ 3e4..6e4 M/extent.  One member 1000 core radii
+    away stretches the extent but stays inside the window (symmetric tickets used); one at 1e7 core
+    radii pushes the central potentials out of it: the halo is then recomputed one-sided in the same
+    pass and the result is still right."""
+    rng = np.random.default_rng(321)
+    n = 70_000
+    st = synth.plummer_stars(n, 2 * synth.KPC, 1e6, rng)
+    for shift, expect_sym in ((2.0, True), (2.0e4, False)):
+        x = st.x.copy()
+        x[12345] += shift
+        args = (x, st.y, st.z, st.vx, st.vy, st.vz, st.mass)
+        one = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=False, kappa=9.0)
+        sym = unbind_halo(*args, mode="fast", max_iter=1, vb_fixed=synth.BULK_V, symmetric=True, kappa=9.0)
+        np.testing.assert_allclose(sym.be32, one.be32, rtol=1e-6)
+        assert np.count_nonzero(sym.mask != one.mask) <= 1
+        if expect_sym:
+            assert sym.stats.evaluations < 0.56 * sym.stats.pairs
+        else:
+            assert sym.stats.evaluations == sym.stats.pairs
