@@ -267,7 +267,8 @@ static int potential_dev(DeviceCtx *c, int mode, const float *sm, const float *s
         CU_TRY(cudaMemsetAsync(out_be, 0, n_tgt * sizeof(float), stream));
         return HALMA_OK;
     }
-    const int variant = potential_pick_variant((n_tgt + 127) / 128, n_src, c->sm_count * c->bps_fast[0] * (kPotentialBlock / 32));
+    const int variant = potential_pick_variant((n_tgt + 127) / 128, n_src, c->sm_count * c->bps_fast[0] * (kPotentialBlock / 32),
+                                               0, false);
     const int group = potential_group_size(mode, variant);
     const int grid = c->sm_count * c->blocks(mode, variant);
     const int S = choose_split(mode, n_tgt, n_src, group, kNominalTickets);
@@ -623,12 +624,13 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     P->n_tot = P->n_pad + P->n_ext_pad;
     if (P->n_tot > 0x7ffffff0ll || P->n_spad > 0x7ffffff0ll || P->n_user == 0) P->np = false;
     {
-        // The predicate-free path pays off once a pass is throughput-bound; below that its
-        // extra tickets and launch only add latency (profiles/ncu_np_r01.md).
+        // The predicate-free path (and with it the symmetric self-term) pays off from ~1e9 pairs per
+        // pass; below that its one-off sort (48 small launches), extra tickets and launch cost more
+        // than they save on a one-shot plan (profiles/midsize_probe_r01.txt).
         double pairs = 0.0;
         for (int64_t h = 0; h < nh; ++h) pairs += static_cast<double>(halo[h].n0) * (halo[h].n0 + halo[h].n_ext);
         const char *e = getenv("HALMA_NP_MIN_PAIRS");
-        const double min_pairs = e ? atof(e) : 4e9;
+        const double min_pairs = e ? atof(e) : 1e9;
         if (pairs < min_pairs) P->np = false;
     }
 
@@ -792,12 +794,14 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.max_iter = cfg.max_iter;
     L.mode = cfg.mode;
     {
-        int64_t g128 = 0, max_src = 0;
+        int64_t g128 = 0, max_src = 0, max_n0 = 0;
         for (int64_t h = 0; h < nh; ++h) {
             g128 += (halo[h].n0 + 127) / 128;
             max_src = std::max<int64_t>(max_src, static_cast<int64_t>(halo[h].n0) + halo[h].n_ext);
+            max_n0 = std::max<int64_t>(max_n0, halo[h].n0);
         }
-        P->variant = potential_pick_variant(g128, max_src, P->ctx->sm_count * P->ctx->bps_fast[0] * (kPotentialBlock / 32));
+        P->variant = potential_pick_variant(g128, max_src, P->ctx->sm_count * P->ctx->bps_fast[0] * (kPotentialBlock / 32),
+                                            max_n0, cfg.symmetric != 0 && P->np && cfg.mode == HALMA_MODE_FAST);
     }
     L.group_size = potential_group_size(cfg.mode, P->variant);
     L.rank = cfg.rank;

@@ -538,7 +538,8 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
                 // symmetric tickets: row tiles x chunks of column tiles (potential.cu::decode_ticket)
                 if (p.sym_enabled) {
                     const int tiles = (n + p.group_size - 1) / p.group_size;
-                    if (tiles >= 2) items += tiles * ((tiles - 1 + kSymChunkTiles - 1) / kSymChunkTiles);
+                    const int ct = sym_chunk_tiles(tiles);
+                    if (tiles >= 2) items += tiles * ((tiles - 1 + ct - 1) / ct);
                 }
             }
         }

@@ -217,7 +217,8 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
     if (!p.sym_enabled || groups < 2) return false;
     // symmetric tickets: (row tile I, chunk c of the tiles J > I); ids of empty chunks are skipped
     local -= 3 * max(myblk, 0);
-    const int chunks = (groups - 1 + kSymChunkTiles - 1) / kSymChunkTiles;
+    const int ct = sym_chunk_tiles(groups);
+    const int chunks = (groups - 1 + ct - 1) / ct;
     if (local >= groups * chunks) return false;
     t.corr_axis = 3;
     t.group = local / chunks;
@@ -438,7 +439,7 @@ __device__ __forceinline__ void correction_ticket(const PotParams &p, const Tick
 // tiles is evaluated ONCE: m_j / r goes to the row particle's sum, m_i / r to the column
 // particle's.  Half the MUFU.RSQ work for the member x member term.
 // The warp holds the 128 members of row tile I in registers (4 per lane) and streams column
-// tiles J > I through the TMA ring.  Inside a tile lanes sweep the 64 source PAIRS in rotation
+// tiles J > I (2 to 32 per ticket, sym_chunk_tiles) through the TMA ring.  Inside a tile lanes sweep the 64 source PAIRS in rotation
 // (lane l visits pair (k + l) mod 64 at step k), so the column partial sums live in shared memory
 // as plain read-modify-writes without conflicts.  Row and column sums are added to phi_sym with
 // float64 atomics whose order is not fixed; the addends are therefore rounded to a per-halo quantum
@@ -509,9 +510,10 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
     const int n = tk.n_tgt;
     const int G = (n + kTileJ - 1) / kTileJ;
     const int I = tk.group;
-    const int j0 = I + 1 + tk.s * kSymChunkTiles;
+    const int ct = sym_chunk_tiles(G);
+    const int j0 = I + 1 + tk.s * ct;
     if (j0 >= G) return;                              // an empty chunk of this row
-    const int j1 = min(j0 + kSymChunkTiles, G);
+    const int j1 = min(j0 + ct, G);
     const F32Set sp = p.src[parity];
     const int64_t base = hd->poff;
     float xi[4], yi[4], zi[4], mi[4];
@@ -936,9 +938,14 @@ int forced_variant()
 
 int potential_num_variants() { return kNumVariants; }
 
-int potential_pick_variant(int64_t groups_of_128, int64_t max_sources, int resident_warps)
+int potential_pick_variant(int64_t groups_of_128, int64_t max_sources, int resident_warps, int64_t max_members,
+                           bool symmetric)
 {
     if (forced_variant() >= 0) return forced_variant();
+    // symmetric tickets need the 128-member tiles of the throughput shape and bring their own
+    // parallelism (tiles^2 / 2 tile pairs in chunks of 2..32): worth it from 64 tiles on
+    // (scripts/probes/midsize_probe.py)
+    if (symmetric && max_members >= 64 * 128) return 0;
     // tickets the throughput shape would have after the j-split (at most kMaxSplit = 8 ways,
     // pieces of >= 2048 sources): if that cannot occupy the resident warps, use small tickets
     int64_t split = max_sources / 2048;

@@ -516,7 +516,7 @@ def test_catalogue_fixed_bulk_velocity_per_halo():
 
 
 def test_predicate_free_path_forced_on_small_and_odd_inputs():
-    """The predicate-free kernel + correction tickets normally engage above 4e9 pairs per pass.
+    """The predicate-free kernel + correction tickets normally engage above 1e9 pairs per pass.
     Re-run the ragged / degenerate / duplicate / NaN / external-group / golden cases with the
     threshold at zero so that every one of them goes through that path."""
     import subprocess
