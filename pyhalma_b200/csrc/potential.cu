@@ -10,11 +10,12 @@
 // complete on a per-stage mbarrier, so no block-wide barrier is ever taken and warps of
 // one block can work on different haloes.
 //
-// Three arithmetic paths share that machinery:
+// Four arithmetic paths share that machinery:
 //
-// EXACT  one target per thread, sources strictly in ascending order, IEEE sqrt and divide,
-//        the reference's != predicate, float32 accumulator: bit-identical to the reference
-//        (see oracle/halma_oracle.c for the contraction of r^2).
+// EXACT  one target per thread, sources strictly in ascending order, IEEE sqrt and divide
+//        (their branch-free fast paths inside a vetted exponent window, the library routines
+//        otherwise), the reference's != predicate, float32 accumulator: bit-identical to the
+//        reference (see oracle/halma_oracle.c for the contraction of r^2).
 //
 // FAST, predicated ("PRED")  per pair of sources and one target: 3 FADD2 + FMUL2 + 2 FFMA2,
 //        2 FMNMX3 + 2 FSETP (min(|dx|,|dy|,|dz|) > 0 <=> all three coordinates differ),
@@ -34,6 +35,10 @@
 //        (zero separation outside the own tile: exact duplicates) flags the halo, which is
 //        then recomputed by the predicated kernel, so correctness never rests on the fast
 //        path.  float32 partial sums over <= 32 sources are flushed into float64.
+//
+// FAST, symmetric self-term ("SYM", on top of NP)  a pair of MEMBERS in different 128-member tiles
+//        is evaluated once and feeds both particles (sym_ticket below): half the MUFU.RSQ work of
+//        the member x member term, exact and therefore order-independent float64 accumulation.
 #include <cstdlib>
 
 #include "halma_common.cuh"
