@@ -616,3 +616,42 @@ def test_symmetric_exact_window_with_far_outliers():
             assert sym.stats.evaluations < 0.56 * sym.stats.pairs
         else:
             assert sym.stats.evaluations == sym.stats.pairs
+
+
+def test_concurrent_plans_from_threads():
+    """Plans are independent objects with their own streams: four host threads unbinding different
+    haloes at the same time must get exactly what a serial run gets (ctypes releases the GIL)."""
+    import threading
+    cases = []
+    for k in range(8):
+        rng = np.random.default_rng(900 + k)
+        st = synth.plummer_stars(3000 + 1700 * k, 2 * synth.KPC, 1e6, rng)
+        gas = synth.lattice_gas(800 + 300 * k, synth.CELL, rng, m_total=3e8)
+        cases.append((st, gas))
+
+    def run(c, mode):
+        st, gas = c
+        return unbind_halo(st.x, st.y, st.z, st.vx, st.vy, st.vz, st.mass, pre=[gas.pos_mass()], kappa=9.0, mode=mode)
+
+    for mode in ("exact", "fast"):
+        serial = [run(c, mode) for c in cases]
+        out = [None] * len(cases)
+        errs = []
+
+        def worker(ids):
+            try:
+                for _ in range(3):
+                    for i in ids:
+                        out[i] = run(cases[i], mode)
+            except Exception as exc:          # surfaces in the main thread below
+                errs.append(exc)
+
+        threads = [threading.Thread(target=worker, args=(list(range(t, len(cases), 4)),)) for t in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errs, errs
+        for a, b in zip(serial, out):
+            assert np.array_equal(a.mask, b.mask) and np.array_equal(a.be32.view(np.uint32), b.be32.view(np.uint32))
+            assert a.n_iter == b.n_iter and a.vb == b.vb
