@@ -133,6 +133,7 @@ def shared_comm(rank, world, device):
 
 
 SYMMETRIC = True      # set from --symmetric
+E2E_STREAMS = 3       # parts of a catalogue in the one-shot (e2e) call, --e2e-streams
 
 
 def make_plan(job, mode, device, rank=0, world=1, upload=True, symmetric=None):
@@ -282,12 +283,20 @@ def e2e_step(jobs_pinned, mode, device, rank=0, world=1):
     """One step through the public plan API from host buffers: create, H2D, run, D2H, destroy."""
     pairs = h2d = d2h = 0
     for job in jobs_pinned:
-        plan = make_plan(job, mode, device, rank, world, upload=True)
-        try:
-            st = plan.run()
-            plan.download()
-        finally:
-            plan.close()
+        if job["kind"] == "catalogue" and E2E_STREAMS > 1:
+            # the one-shot catalogue call with its parts overlapped on separate streams / host threads
+            from pyhalma_b200.unbind import unbind_catalogue
+            kw = job["kw"]
+            st = unbind_catalogue(job["offsets"], *job["members"], groups=job["groups"], n_pre=kw["n_pre"],
+                                  split_classes=kw["split_classes"], vb=kw["vb"], kappa=kw["kappa"], max_iter=64,
+                                  mode=mode, device=device, symmetric=SYMMETRIC, streams=E2E_STREAMS).stats
+        else:
+            plan = make_plan(job, mode, device, rank, world, upload=True)
+            try:
+                st = plan.run()
+                plan.download()
+            finally:
+                plan.close()
         n = len(job["members"][0])
         pairs += st.pairs // world if (job["split"] and world > 1) else st.pairs
         h2d += 7 * 8 * n + sum(4 * 8 * len(g[1]) for g in job["groups"])
@@ -455,8 +464,9 @@ def run_gpu(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_pairs_all / e2e_s_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "how": "public plan API per job, everything inside the timing: plan create + H2D from pinned "
-                           "host + device loop + D2H of mask, potentials, energies, member lists + destroy"},
+                    "how": "public plan API per job (catalogue jobs: unbind_catalogue with %d overlapped parts), "
+                           "everything inside the timing: plan create + H2D from pinned host + device loop + D2H of "
+                           "mask, potentials, energies, member lists + destroy" % E2E_STREAMS},
             "gpu_launches": int(launches_all),
             "one_sided": None if one_sided is None else {
                 "value": one_sided[2] / (one_sided[0] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": one_sided[0] / one_sided[3],
@@ -484,6 +494,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--e2e-streams", type=int, default=3,
+                    help="catalogue workloads: parts of the one-shot call that overlap upload, sort and download")
     ap.add_argument("--symmetric", type=int, default=1, choices=[0, 1],
                     help="evaluate member x member pairs once for both particles (FAST mode, not in split mode)")
     ap.add_argument("--cpu-targets", type=int, default=60000, help="targets per job in the cpu_baseline sample")
@@ -494,8 +506,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    global SYMMETRIC
+    global SYMMETRIC, E2E_STREAMS
     SYMMETRIC = bool(args.symmetric) and args.mode == "fast"
+    E2E_STREAMS = max(1, args.e2e_streams)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -472,7 +472,8 @@ __global__ void __launch_bounds__(kCh) k_compact(const LoopParams p)
 __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
 {
     __shared__ int sred[33];
-    __shared__ int s_total_groups, s_carry, s_any;
+    __shared__ long long spair[32];
+    __shared__ int s_total_groups, s_carry, s_any, s_sym_chunk;
     LoopState *st = p.st;
     if (!init && !st->any_active) {
         // graph driver: nothing left to do, leave the WHILE node
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // commit
     int groups = 0, any = 0;
+    long long tile_pairs = 0;          // symmetric tickets: off-diagonal tile pairs of the whole plan
     for (int h = threadIdx.x; h < p.n_halo; h += blockDim.x) {
         if (init || p.active[h]) {
             // the halo took part in this pass: its members now live in the other buffer
@@ -495,13 +497,21 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
         if (p.active[h]) {
             // all ranks' groups: the j-split must depend on the problem only, so that a split
             // run sums its partial potentials in the same grouping as a single-GPU run
-            groups += (p.cnt[h] + p.group_size - 1) / p.group_size;
+            const long long tiles = (p.cnt[h] + p.group_size - 1) / p.group_size;
+            groups += static_cast<int>(tiles);
+            tile_pairs += tiles * (tiles - 1) / 2;
             any = 1;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) groups += __shfl_down_sync(0xffffffffu, groups, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        groups += __shfl_down_sync(0xffffffffu, groups, o);
+        tile_pairs += __shfl_down_sync(0xffffffffu, tile_pairs, o);
+    }
     any = __any_sync(0xffffffffu, any);
-    if (lane == 0) sred[warp] = groups;
+    if (lane == 0) {
+        sred[warp] = groups;
+        spair[warp] = tile_pairs;
+    }
     if (threadIdx.x == 0) {
         s_any = 0;
         s_carry = 0;
@@ -510,11 +520,22 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
     if (lane == 0 && any) atomicOr(&s_any, 1);
     if (threadIdx.x == 0) {
         int t = 0;
-        for (int w = 0; w < 32; ++w) t += sred[w];
+        long long tp = 0;
+        for (int w = 0; w < 32; ++w) {
+            t += sred[w];
+            tp += spair[w];
+        }
         s_total_groups = t;
+        // column tiles per symmetric ticket: about kNominalTickets tickets over the whole plan, between
+        // 2 and 32 -- a lone mid-size halo gets short tickets that fill the machine, a catalogue or a giant
+        // halo long ones that amortise the per-ticket work.  Depends on the plan only, not on the GPU.
+        const long long c = tp / kNominalTickets;
+        s_sym_chunk = c < 2 ? 2 : (c > 32 ? 32 : static_cast<int>(c));
+        st->sym_chunk = s_sym_chunk;
     }
     __syncthreads();
     const int total_groups = s_total_groups;
+    const int sym_chunk = s_sym_chunk;
     int want = 1;
     if (p.mode == HALMA_MODE_FAST && total_groups > 0 && total_groups < p.target_items)
         want = (p.target_items + total_groups - 1) / total_groups;
@@ -538,8 +559,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
                 // symmetric tickets: row tiles x chunks of column tiles (potential.cu::decode_ticket)
                 if (p.sym_enabled) {
                     const int tiles = (n + p.group_size - 1) / p.group_size;
-                    const int ct = sym_chunk_tiles(tiles);
-                    if (tiles >= 2) items += tiles * ((tiles - 1 + ct - 1) / ct);
+                    if (tiles >= 2) items += tiles * ((tiles - 1 + sym_chunk - 1) / sym_chunk);
                 }
             }
         }

@@ -222,7 +222,7 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
     if (!p.sym_enabled || groups < 2) return false;
     // symmetric tickets: (row tile I, chunk c of the tiles J > I); ids of empty chunks are skipped
     local -= 3 * max(myblk, 0);
-    const int ct = sym_chunk_tiles(groups);
+    const int ct = p.st->sym_chunk;
     const int chunks = (groups - 1 + ct - 1) / ct;
     if (local >= groups * chunks) return false;
     t.corr_axis = 3;
@@ -444,7 +444,7 @@ __device__ __forceinline__ void correction_ticket(const PotParams &p, const Tick
 // tiles is evaluated ONCE: m_j / r goes to the row particle's sum, m_i / r to the column
 // particle's.  Half the MUFU.RSQ work for the member x member term.
 // The warp holds the 128 members of row tile I in registers (4 per lane) and streams column
-// tiles J > I (2 to 32 per ticket, sym_chunk_tiles) through the TMA ring.  Inside a tile lanes sweep the 64 source PAIRS in rotation
+// tiles J > I (2 to 32 per ticket, LoopState::sym_chunk) through the TMA ring.  Inside a tile lanes sweep the 64 source PAIRS in rotation
 // (lane l visits pair (k + l) mod 64 at step k), so the column partial sums live in shared memory
 // as plain read-modify-writes without conflicts.  Row and column sums are added to phi_sym with
 // float64 atomics whose order is not fixed; the addends are therefore rounded to a per-halo quantum
@@ -515,7 +515,7 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
     const int n = tk.n_tgt;
     const int G = (n + kTileJ - 1) / kTileJ;
     const int I = tk.group;
-    const int ct = sym_chunk_tiles(G);
+    const int ct = p.st->sym_chunk;
     const int j0 = I + 1 + tk.s * ct;
     if (j0 >= G) return;                              // an empty chunk of this row
     const int j1 = min(j0 + ct, G);

@@ -275,6 +275,14 @@ class UnbindPlan:
         return RunStats(st.total_ms, st.potential_ms, st.potential_launches, st.launches, st.passes, st.pairs,
                         st.evaluations)
 
+    def download_into(self, mask_addr=0, be_addr=0, energy_addr=0, idx_addr=0, halos_addr=0) -> None:
+        """halma_plan_download into caller-owned host memory (raw addresses; 0 = skip): mask uint8[n],
+        be float32[n], energy float64[n], idx int32[n], halos halma_halo_result[n_halo]."""
+        def vp(a):
+            return C.c_void_p(int(a)) if a else None
+        _lib.check(self._L.halma_plan_download(self._h, vp(mask_addr), vp(be_addr), vp(energy_addr), vp(idx_addr),
+                                               C.cast(vp(halos_addr), C.POINTER(_lib.HaloResult)) if halos_addr else None))
+
     def download(self, mask=True, be=True, energy=True, idx=True, halos=True) -> CatalogueResult:
         n = self.n
         # result arrays live in pooled page-locked memory: D2H at link speed, no page faults
@@ -326,14 +334,23 @@ def nccl_unique_id() -> bytes:
 def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (), n_pre: int = 0,
                      split_classes: bool = False, vb=None, kappa: float = 9.0, max_iter: int = 64,
                      mode="fast", device: int = 0, G: float = G_CONST, temp=None,
-                     cold_T: float = 5 * 1e4, symmetric: Optional[bool] = None) -> CatalogueResult:
+                     cold_T: float = 5 * 1e4, symmetric: Optional[bool] = None, streams: int = 1) -> CatalogueResult:
     """Unbind every halo of a catalogue in one batched, device-resident run.
 
     groups: sequence of (ext_offsets, mass, x, y, z) external source groups.
     vb: None (bulk velocity recomputed from the bound set each pass) or float64[n_halo, 3].
     temp: optional member temperatures; fills the cold / hot mass sums of every HaloResult.
     symmetric: evaluate member x member pairs once for both particles (halma_unbind_config.symmetric).
+    streams: > 1 cuts the catalogue into that many runs of consecutive haloes of about equal cost,
+        each with its own plan and host thread, so that the upload, sort and download of one part
+        overlap the device loop of another (haloes are independent; in FAST mode the j-split of a
+        halo can differ from the one-plan run, i.e. potentials agree to ~1e-16 before their float32
+        rounding rather than always bit for bit; EXACT mode is bit-identical).
     """
+    offsets = _i64(offsets)
+    if streams > 1 and len(offsets) - 1 >= 2 * streams:
+        return _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, split_classes, vb, kappa,
+                                       max_iter, mode, device, G, temp, cold_T, symmetric, streams)
     plan = UnbindPlan(offsets, [g[0] for g in groups], mode=mode, n_pre=n_pre, split_classes=split_classes,
                       vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa, device=device,
                       symmetric=symmetric)
@@ -351,6 +368,72 @@ def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (
         return res
     finally:
         plan.close()
+
+
+def cost_cuts(offsets, ext_offsets, parts: int) -> list:
+    """Halo indices that cut a catalogue into at most `parts` runs of consecutive haloes of about
+    equal cost N_h (N_h + N_ext,h): [0, ..., n_halo], strictly increasing."""
+    offsets = _i64(offsets)
+    nh = len(offsets) - 1
+    nmem = np.diff(offsets).astype(np.float64)
+    next_ = sum((np.diff(_i64(e)).astype(np.float64) for e in ext_offsets), np.zeros(nh))
+    cum = np.concatenate(([0.0], np.cumsum(nmem * (nmem + next_))))
+    cuts = [0] + [int(np.searchsorted(cum, cum[-1] * k / parts)) for k in range(1, parts)] + [nh]
+    return sorted(set(min(max(c, 0), nh) for c in cuts))
+
+
+def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, split_classes, vb, kappa, max_iter,
+                            mode, device, G, temp, cold_T, symmetric, streams) -> CatalogueResult:
+    import threading
+    nh = len(offsets) - 1
+    n = int(offsets[-1])
+    members = [_f64(a) for a in (x, y, z, vx, vy, vz, mass)]
+    groups = [(_i64(g[0]),) + tuple(_f64(a) for a in g[1:]) for g in groups]
+    vb = None if vb is None else np.ascontiguousarray(vb, dtype=np.float64).reshape(nh, 3)
+    temp = None if temp is None else _f64(temp)
+    cuts = cost_cuts(offsets, [g[0] for g in groups], streams)
+    out_mask = _lib.pinned_empty(n, np.uint8)
+    out_be = _lib.pinned_empty(n, np.float32)
+    out_energy = _lib.pinned_empty(n, np.float64)
+    out_idx = _lib.pinned_empty(n, np.int32)
+    raw = (_lib.HaloResult * max(1, nh))()
+    stats: list = [None] * (len(cuts) - 1)
+    errors: list = []
+
+    def part(k):
+        try:
+            a, b = cuts[k], cuts[k + 1]
+            o0, o1 = int(offsets[a]), int(offsets[b])
+            sub = [(g[0][a:b + 1] - g[0][a],) + tuple(arr[int(g[0][a]):int(g[0][b])] for arr in g[1:]) for g in groups]
+            with UnbindPlan(offsets[a:b + 1] - o0, [g[0] for g in sub], mode=mode, n_pre=n_pre,
+                            split_classes=split_classes, vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa,
+                            device=device, symmetric=symmetric) as plan:
+                plan.upload_members(*[m[o0:o1] for m in members])
+                for gi, g in enumerate(sub):
+                    plan.upload_group(gi, g[1], g[2], g[3], g[4])
+                if vb is not None:
+                    plan.set_vb(vb[a:b])
+                if temp is not None:
+                    plan.upload_temp(temp[o0:o1], cold_T)
+                stats[k] = plan.run()
+                plan.download_into(out_mask.ctypes.data + o0, out_be.ctypes.data + 4 * o0,
+                                   out_energy.ctypes.data + 8 * o0, out_idx.ctypes.data + 4 * o0,
+                                   C.addressof(raw) + a * C.sizeof(_lib.HaloResult))
+        except Exception as exc:          # re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=part, args=(k,)) for k in range(len(cuts) - 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    res = CatalogueResult(offsets, out_mask, out_be, out_energy, out_idx, HaloResults(raw, nh))
+    res.stats = RunStats(max(s.total_ms for s in stats), sum(s.potential_ms for s in stats),
+                         sum(s.potential_launches for s in stats), sum(s.launches for s in stats),
+                         max(s.passes for s in stats), sum(s.pairs for s in stats), sum(s.evaluations for s in stats))
+    return res
 
 
 def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence = (),

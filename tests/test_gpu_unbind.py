@@ -655,3 +655,42 @@ def test_concurrent_plans_from_threads():
         for a, b in zip(serial, out):
             assert np.array_equal(a.mask, b.mask) and np.array_equal(a.be32.view(np.uint32), b.be32.view(np.uint32))
             assert a.n_iter == b.n_iter and a.vb == b.vb
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_multi_stream_catalogue_matches_one_plan(mode):
+    """unbind_catalogue(streams=3): consecutive runs of haloes in their own plans and host threads.
+    EXACT is bit-identical to the one-plan run; FAST may differ where a halo's j-split differs."""
+    cat = synth.config3(n_halo=60, nmin=50, nmax=9000, seed_extra=4)
+    args = (cat.offsets, cat.x, cat.y, cat.z, cat.vx, cat.vy, cat.vz, cat.mass)
+    one = unbind_catalogue(*args, mode=mode)
+    par = unbind_catalogue(*args, mode=mode, streams=3)
+    assert len(par.halos) == len(one.halos) == 60
+    assert [h.n_iter for h in par.halos] == [h.n_iter for h in one.halos]
+    assert list(par.halos.field("n_bound")) == [h.n_bound for h in one.halos]
+    assert par.stats.pairs == one.stats.pairs
+    if mode == "exact":
+        assert np.array_equal(par.be32.view(np.uint32), one.be32.view(np.uint32))
+        assert np.array_equal(par.mask, one.mask) and np.array_equal(par.energy, one.energy)
+        for h in (0, 17, 59):
+            assert np.array_equal(par.members(h), one.members(h)) and par.halos[h].vb == one.halos[h].vb
+    else:
+        np.testing.assert_allclose(par.be32, one.be32, rtol=1e-6)
+        assert np.count_nonzero(par.mask != one.mask) == 0
+    # with an external group and fixed bulk velocities
+    rng = np.random.default_rng(5)
+    nh = cat.n_halo
+    ext_n = rng.integers(0, 40, nh)
+    eoff = np.concatenate(([0], np.cumsum(ext_n)))
+    centres = np.array([[cat.x[cat.offsets[h]], cat.y[cat.offsets[h]], cat.z[cat.offsets[h]]] for h in range(nh)])
+    rep = np.repeat(np.arange(nh), ext_n)
+    ex, ey, ez = (centres[rep, k] + rng.normal(0, 2e-3, len(rep)) for k in range(3))
+    em = rng.uniform(1e6, 1e8, len(rep))
+    vb = rng.normal(0, 100, (nh, 3))
+    kw = dict(groups=[(eoff, em, ex, ey, ez)], n_pre=0, split_classes=True, vb=vb, kappa=2.0, mode=mode)
+    one = unbind_catalogue(*args, **kw)
+    par = unbind_catalogue(*args, streams=4, **kw)
+    if mode == "exact":
+        assert np.array_equal(par.be32.view(np.uint32), one.be32.view(np.uint32)) and np.array_equal(par.mask, one.mask)
+    else:
+        np.testing.assert_allclose(par.be32, one.be32, rtol=1e-6)

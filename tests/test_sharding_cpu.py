@@ -134,3 +134,21 @@ def test_split_protocol_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(results)
+
+
+def test_cost_cuts_for_the_multi_stream_catalogue_path():
+    from pyhalma_b200.unbind import cost_cuts
+    sizes = np.array([10, 10, 1000, 10, 10, 10, 500, 500, 10, 10])
+    off = np.concatenate(([0], np.cumsum(sizes)))
+    cuts = cost_cuts(off, [], 3)
+    assert cuts[0] == 0 and cuts[-1] == len(sizes) and all(b > a for a, b in zip(cuts, cuts[1:])) and len(cuts) <= 4
+    cost = sizes.astype(float) ** 2
+    parts = [cost[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+    assert max(parts) <= 1.0 * cost.sum()          # the giant halo bounds any partition of consecutive runs
+    assert cost_cuts(off, [], 1) == [0, len(sizes)]
+    # externals count: a halo with many external sources is as expensive as a bigger one
+    ext = np.concatenate(([0], np.cumsum(np.where(np.arange(10) == 0, 10_000_000, 0))))
+    assert cost_cuts(off, [ext], 2)[1] == 1
+    # equal haloes split evenly
+    off = np.arange(0, 1201, 100)
+    assert cost_cuts(off, [], 4) == [0, 3, 6, 9, 12]
