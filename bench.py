@@ -133,22 +133,32 @@ def shared_comm(rank, world, device):
 
 
 SYMMETRIC = True      # set from --symmetric
+REUSE = None          # set from --reuse: external-sum cache + incremental passes (None: the library default)
 E2E_STREAMS = 3       # parts of a catalogue in the one-shot (e2e) call, --e2e-streams
 
 
-def make_plan(job, mode, device, rank=0, world=1, upload=True, symmetric=None):
+def make_plan(job, mode, device, rank=0, world=1, upload=True, symmetric=None, reuse="default"):
     from pyhalma_b200.unbind import UnbindPlan
     kw = job["kw"]
     split = job["split"] and world > 1
     plan = UnbindPlan(job["offsets"], [g[0] for g in job["groups"]], mode=mode, n_pre=kw["n_pre"],
                       split_classes=kw["split_classes"], vb_fixed=kw["vb"] is not None, max_iter=64,
                       kappa=kw["kappa"], device=device, rank=rank if split else 0, n_ranks=world if split else 1,
-                      symmetric=SYMMETRIC if symmetric is None else symmetric)
+                      symmetric=SYMMETRIC if symmetric is None else symmetric,
+                      cache_external=REUSE if reuse == "default" else reuse,
+                      incremental=REUSE if reuse == "default" else reuse)
     if split:
         plan.use_comm(shared_comm(rank, world, device))
     if upload:
         upload_job(plan, job)
     return plan
+
+
+def reuse_requested() -> bool:
+    from pyhalma_b200 import unbind as _unbind
+    if REUSE is not None:
+        return bool(REUSE)
+    return _unbind._reuse_default("HALMA_CACHE_EXT") or _unbind._reuse_default("HALMA_INCREMENTAL")
 
 
 def upload_job(plan, job):
@@ -289,7 +299,8 @@ def e2e_step(jobs_pinned, mode, device, rank=0, world=1):
             kw = job["kw"]
             st = unbind_catalogue(job["offsets"], *job["members"], groups=job["groups"], n_pre=kw["n_pre"],
                                   split_classes=kw["split_classes"], vb=kw["vb"], kappa=kw["kappa"], max_iter=64,
-                                  mode=mode, device=device, symmetric=SYMMETRIC, streams=E2E_STREAMS).stats
+                                  mode=mode, device=device, symmetric=SYMMETRIC, streams=E2E_STREAMS,
+                                  cache_external=REUSE, incremental=REUSE).stats
         else:
             plan = make_plan(job, mode, device, rank, world, upload=True)
             try:
@@ -378,10 +389,10 @@ def run_gpu(args, rank, local_rank, world):
 
     # the same workload with one-sided sums only (symmetric = 0): evaluations == interactions
     one_sided = None
-    if SYMMETRIC:
+    if SYMMETRIC or reuse_requested():
         for p in plans:
             p.close()
-        plans = [make_plan(j, mode, local_rank, rank, world, symmetric=False) for j in jobs]
+        plans = [make_plan(j, mode, local_rank, rank, world, symmetric=False, reuse=False) for j in jobs]
         step()
         barrier()
         o_ms = o_pot = 0.0
@@ -404,6 +415,7 @@ def run_gpu(args, rank, local_rank, world):
     dev_ms_max, wall_ms_max, e2e_s_max, pot_ms_max = t.tolist()
     pairs_all, e2e_pairs_all, launches_all = w.tolist()
 
+    reuse_on = reuse_requested() and mode == "fast"
     if rank == 0:
         peaks = {}
         try:
@@ -458,7 +470,8 @@ def run_gpu(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(desc, mode=mode, l2="flushed between steps (256 MiB write)",
-                           passes_per_step=passes / args.steps, symmetric_self_term=bool(SYMMETRIC)),
+                           passes_per_step=passes / args.steps, symmetric_self_term=bool(SYMMETRIC),
+                           reuse=reuse_on),
             "wall_ms_per_step": wall_ms_max / args.steps,
             "interactions_per_step": pairs_all / args.steps,
             "clocks": clocks,
@@ -472,8 +485,8 @@ def run_gpu(args, rank, local_rank, world):
                 "value": one_sided[2] / (one_sided[0] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": one_sided[0] / one_sided[3],
                 "kernel": one_sided[2] / (one_sided[1] * 1e-3) / 1e9, "roofline_frac": one_sided[2] / (one_sided[1] * 1e-3) / 1e9 / peak,
                 "scope": "rank 0" if world > 1 else "whole job", "steps": one_sided[3],
-                "note": "same workload with halma_unbind_config.symmetric = 0: every interaction is its own 1/r "
-                        "evaluation and results are bit-reproducible"},
+                "note": "same workload with halma_unbind_config.symmetric = cache_external = incremental = 0: every "
+                        "interaction the reference's loop visits is evaluated, in every pass"},
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
@@ -498,6 +511,9 @@ def main():
                     help="catalogue workloads: parts of the one-shot call that overlap upload, sort and download")
     ap.add_argument("--symmetric", type=int, default=1, choices=[0, 1],
                     help="evaluate member x member pairs once for both particles (FAST mode, not in split mode)")
+    ap.add_argument("--reuse", type=int, default=None, choices=[0, 1],
+                    help="do not repeat work between passes: external sums cached, incremental passes (FAST mode; "
+                         "default: the library's, HALMA_CACHE_EXT / HALMA_INCREMENTAL)")
     ap.add_argument("--cpu-targets", type=int, default=60000, help="targets per job in the cpu_baseline sample")
     ap.add_argument("--ref-targets", type=int, default=20000, help="targets per job per step of --impl reference")
     args = ap.parse_args()
@@ -506,7 +522,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    global SYMMETRIC, E2E_STREAMS
+    global SYMMETRIC, E2E_STREAMS, REUSE
+    REUSE = None if args.reuse is None else bool(args.reuse)
     SYMMETRIC = bool(args.symmetric) and args.mode == "fast"
     E2E_STREAMS = max(1, args.e2e_streams)
     if args.impl == "reference":

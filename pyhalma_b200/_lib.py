@@ -41,7 +41,8 @@ class UnbindConfig(C.Structure):
                 ("n_groups", C.c_int32), ("n_pre", C.c_int32), ("split_classes", C.c_int32),
                 ("vb_fixed", C.c_int32), ("max_iter", C.c_int32), ("G", C.c_double),
                 ("kappa", C.c_double), ("rank", C.c_int32), ("n_ranks", C.c_int32),
-                ("use_graph", C.c_int32), ("symmetric", C.c_int32)]
+                ("use_graph", C.c_int32), ("symmetric", C.c_int32),
+                ("cache_external", C.c_int32), ("incremental", C.c_int32)]
 
 
 class HaloResult(C.Structure):

@@ -476,6 +476,11 @@ struct halma_plan {
     DBuf<unsigned long long> d_pairs, d_evals;
     DBuf<double> d_phi_sym, d_symq;
     bool sym = false;
+    // external-sum cache and incremental passes (FAST predicate-free path, one GPU)
+    bool cache_ext = false, incr = false;
+    DBuf<double> d_phi_ext, d_phi_self;
+    DBuf<float> d_rem;                    // 4 * n_pad: members removed by the last pass (x y z m)
+    DBuf<int32_t> d_reuse_int;            // ext_ok, incr, rem_cnt: 3 * n_halo
     DBuf<int32_t> d_cint;                 // per-chunk ints: cnt, off
     DBuf<double> d_csum;                  // kChunkSums per chunk
     DBuf<float> d_cbest;
@@ -527,6 +532,7 @@ struct halma_plan {
         d_src_halo.release(); d_sslot.release(); d_stgt.release(); d_sinv.release(); d_redo.release();
         d_nsel.release(); d_keys.release(); d_ids.release(); d_skey.release(); d_ismem.release();
         d_sorttemp.release(); d_sf.release(); d_corr.release();
+        d_phi_ext.release(); d_phi_self.release(); d_rem.release(); d_reuse_int.release();
     }
     ~halma_plan()
     {
@@ -824,6 +830,28 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.sym_enabled = P->sym ? 1 : 0;
     L.sym_ext = P->d_symq.p;
     L.sym_q = P->sym ? P->d_symq.p + nh : nullptr;
+    // External-sum cache and incremental passes ride on the predicate-free path (whose sums are kept per
+    // member in float64 and whose excluded pairs are handled by the correction tickets every pass).  Not in
+    // split mode: the kept sums would need their own all-reduce.
+    P->cache_ext = cfg.cache_external && P->np && cfg.n_ranks == 1 && P->max_ext > 0;
+    P->incr = cfg.incremental && P->np && cfg.n_ranks == 1;
+    if (P->cache_ext || P->incr) CU_TRY(P->d_reuse_int.alloc(3 * std::max<size_t>(nh, 1)));
+    if (P->cache_ext) CU_TRY(P->d_phi_ext.alloc(planes * NP));
+    if (P->incr) {
+        CU_TRY(P->d_phi_self.alloc(NP));
+        CU_TRY(P->d_rem.alloc(4 * NP));
+    }
+    L.phi_ext = P->d_phi_ext.p;
+    L.ext_ok = P->d_reuse_int.p;
+    L.cache_ext = P->cache_ext ? 1 : 0;
+    L.phi_self = P->d_phi_self.p;
+    L.rx = P->d_rem.p;
+    L.ry = P->incr ? P->d_rem.p + NP : nullptr;
+    L.rz = P->incr ? P->d_rem.p + 2 * NP : nullptr;
+    L.rm = P->incr ? P->d_rem.p + 3 * NP : nullptr;
+    L.incr = P->d_reuse_int.p ? P->d_reuse_int.p + nh : nullptr;
+    L.rem_cnt = P->d_reuse_int.p ? P->d_reuse_int.p + 2 * nh : nullptr;
+    L.incr_enabled = P->incr ? 1 : 0;
 
     PotParams &Q = P->pp;
     memset(&Q, 0, sizeof Q);
@@ -853,6 +881,13 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     Q.phi_sym = P->d_phi_sym.p;
     Q.sym_q = L.sym_q;
     Q.sym_enabled = P->sym ? 1 : 0;
+    Q.phi_ext = L.phi_ext;
+    Q.ext_ok = L.ext_ok;
+    Q.cache_ext = L.cache_ext;
+    Q.incr = L.incr;
+    Q.rem_cnt = L.rem_cnt;
+    Q.incr_enabled = L.incr_enabled;
+    Q.src[6] = F32Set{L.rx, L.ry, L.rz, L.rm};
     for (int a = 0; a < 3 && P->np; ++a) {
         Q.ax[a] = L.ax[a];
         Q.src[3 + a] = F32Set{P->sax[a].x, P->sax[a].y, P->sax[a].z, P->sax[a].m};

@@ -215,10 +215,28 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
             const int S = p.nsplit[h];
             double phi = p.phi_part[i];
             for (int k = 1; k < S; ++k) phi += p.phi_part[static_cast<int64_t>(k) * p.n_pad + i];
-            if (p.sym_enabled && !p.halo_redo[h]) phi += p.phi_sym[i];
-            if (p.np_enabled && !p.halo_redo[h]) {
+            // a halo handed to the predicated kernel has its complete, final sum in the planes
+            const bool redo = p.np_enabled && p.halo_redo[h];
+            const bool inc = p.incr_enabled && p.incr[h];
+            const int64_t slot = hd.poff + (g - hd.uoff);      // the member's original slot
+            if (p.sym_enabled && !redo && !inc) phi += p.phi_sym[i];
+            if (p.incr_enabled && !redo) {
+                // incremental pass: the planes hold the sum over the members the previous pass removed;
+                // take it out of the predicate-free sum kept from that pass
+                if (inc) phi = p.phi_self[slot] - phi;
+                p.phi_self[slot] = phi;
+            }
+            if (p.cache_ext && hd.n_ext > 0 && !redo && p.ext_ok[h]) {
+                // sum over the external sources, evaluated by the first pass only (potential.cu)
+                if (p.st->pass == 0) {
+                    double e = p.phi_ext[slot];
+                    for (int k = 1; k < S; ++k) e += p.phi_ext[static_cast<int64_t>(k) * p.n_pad + slot];
+                    p.phi_ext[slot] = e;
+                }
+                phi += p.phi_ext[slot];
+            }
+            if (p.np_enabled && !redo) {
                 // predicate-free path: take out the pairs that share a coordinate (potential.cu)
-                const int64_t slot = hd.poff + (g - hd.uoff);
                 phi -= (p.ax[0].corr[slot] + p.ax[1].corr[slot]) + p.ax[2].corr[slot];
             }
             const float be = __double2float_rn(phi);
@@ -396,19 +414,42 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
                 p.pairs[h] = 0ull;
                 p.evals[h] = 0ull;
                 act = (n_new > 0 && p.max_iter > 0) ? 1 : 0;
+                if (p.cache_ext) p.ext_ok[h] = 1;
+                if (p.incr_enabled) {
+                    p.incr[h] = 0;
+                    p.rem_cnt[h] = 0;
+                }
             } else {
                 const int it = p.iter[h] + 1;
                 p.iter[h] = it;
                 const unsigned long long nn = static_cast<unsigned long long>(n_old);
                 p.pairs[h] += nn * static_cast<unsigned long long>(n_old + hd.n_ext);
                 const unsigned long long tiles = (nn + p.group_size - 1) / p.group_size;
-                if (p.sym_enabled && tiles >= 2 && !p.halo_redo[h]) {
+                const bool redo = p.np_enabled && p.halo_redo[h];
+                const bool was_incr = p.incr_enabled && p.incr[h] && !redo;
+                // externals: evaluated unless their first-pass sum was reused (cache) or kept (incremental)
+                const bool ext_reused = p.cache_ext && p.st->pass > 0 && p.ext_ok[h] && !redo;
+                const unsigned long long ext_ev = ext_reused ? 0ull : nn * static_cast<unsigned long long>(hd.n_ext);
+                if (was_incr) {
+                    // survivors x the members the previous pass removed
+                    p.evals[h] += nn * static_cast<unsigned long long>(p.rem_cnt[h]);
+                } else if (p.sym_enabled && tiles >= 2 && !redo) {
                     // diagonal tiles one-sided, every other member pair once
                     const unsigned long long last = nn - (tiles - 1) * p.group_size;
                     const unsigned long long diag = (tiles - 1) * p.group_size * p.group_size + last * last;
-                    p.evals[h] += nn * hd.n_ext + (nn * nn + diag) / 2;
+                    p.evals[h] += ext_ev + (nn * nn + diag) / 2;
                 } else {
-                    p.evals[h] += nn * static_cast<unsigned long long>(n_old + hd.n_ext);
+                    p.evals[h] += nn * nn + ext_ev;
+                }
+                // a first pass that fell back to the predicated kernel leaves no usable external sums
+                if (p.cache_ext && p.st->pass == 0 && redo) p.ext_ok[h] = 0;
+                if (p.incr_enabled) {
+                    // The coming pass is incremental when this one left a valid predicate-free sum behind
+                    // (k_energy_flag, phi_self) and removed at most a third of the members: survivors x removed
+                    // is then cheaper than a full pass even with the symmetric self-term.
+                    const int n_rem = n_old - n_new;
+                    p.rem_cnt[h] = n_rem;
+                    p.incr[h] = (!redo && n_rem > 0 && 2ll * n_rem <= n_new) ? 1 : 0;
                 }
                 const int changed = n_new != n_old;
                 p.converged[h] = (!changed || n_new == 0) ? 1 : 0;
@@ -452,6 +493,14 @@ __global__ void __launch_bounds__(kCh) k_compact(const LoopParams p)
             const int64_t slot = hd.poff + (p.widx[par][i] - hd.uoff);
 #pragma unroll
             for (int a = 0; a < 3; ++a) p.ax[a].m[p.ax[a].inv[slot]] = 0.f;
+        }
+        if (p.incr_enabled && p.incr[h] && q < n && !f) {
+            // the coming pass is incremental: keep the removed members, in order, as its sources
+            const int64_t d = hd.poff + (q - (p.chunk_off[c] + base + rank_in_warp));
+            p.rx[d] = p.wx[par][i];
+            p.ry[d] = p.wy[par][i];
+            p.rz[d] = p.wz[par][i];
+            p.rm[d] = p.wm[par][i];
         }
         if (f) {
             const int64_t d = hd.poff + p.chunk_off[c] + base + rank_in_warp;
@@ -499,7 +548,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
             // run sums its partial potentials in the same grouping as a single-GPU run
             const long long tiles = (p.cnt[h] + p.group_size - 1) / p.group_size;
             groups += static_cast<int>(tiles);
-            tile_pairs += tiles * (tiles - 1) / 2;
+            if (!(p.incr_enabled && !init && p.incr[h])) tile_pairs += tiles * (tiles - 1) / 2;
             any = 1;
         }
     }
@@ -549,7 +598,11 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
             h = p.order[k];
             if (p.active[h]) {
                 const int n = p.cnt[h];
-                const int n_src = n + p.halo[h].n_ext;
+                // sources a main ticket of the coming pass streams (potential.cu): the removed members in an
+                // incremental pass, else the members plus the externals unless their sum is cached
+                const bool inc = p.incr_enabled && !init && p.incr[h];
+                const bool ext_cached = p.cache_ext && !init && p.ext_ok[h];
+                const int n_src = inc ? p.rem_cnt[h] : n + (ext_cached ? 0 : p.halo[h].n_ext);
                 int S = min(want, min(p.max_split, max(1, n_src / kMinSplitSources)));
                 p.nsplit[h] = S;
                 max_split = max(max_split, S);
@@ -557,7 +610,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
                 // correction tickets: three axes x blocks of the (static) sorted member list
                 if (p.np_enabled) items += 3 * my_groups(p.halo[h].n0, p.group_size, p.rank, p.n_ranks);
                 // symmetric tickets: row tiles x chunks of column tiles (potential.cu::decode_ticket)
-                if (p.sym_enabled) {
+                if (p.sym_enabled && !inc) {
                     const int tiles = (n + p.group_size - 1) / p.group_size;
                     if (tiles >= 2) items += tiles * ((tiles - 1 + sym_chunk - 1) / sym_chunk);
                 }

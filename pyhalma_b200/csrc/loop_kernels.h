@@ -58,6 +58,16 @@ struct LoopParams {
     int32_t sym_enabled;
     double *sym_ext;                      // [n_halo] largest coordinate extent of the halo's members
     double *sym_q;                        // [n_halo] quantum of the symmetric sums for the coming pass
+    // external-sum cache (potential.cu, main tickets): first-pass sums over the external sources
+    double *phi_ext;                      // [max_split][n_pad] by original slot; plane 0 holds the folded sum
+    int32_t *ext_ok;                      // [n_halo] 1: phi_ext of this halo is valid
+    int32_t cache_ext;
+    // incremental passes: kept predicate-free self-term, members removed by the previous pass
+    double *phi_self;                     // [n_pad] by original slot
+    float *rx, *ry, *rz, *rm;             // [n_pad] removed members of the last pass, per halo at poff
+    int32_t *rem_cnt;                     // [n_halo]
+    int32_t *incr;                        // [n_halo] the coming / current pass of the halo is incremental
+    int32_t incr_enabled;
     // CUDA-graph loop driver: conditional handle of the WHILE node (0 = not in a graph)
     unsigned long long cond_handle;
 };

@@ -67,11 +67,17 @@ struct TileCursor {
     int64_t base;
     int set, pos, end, flags;
     int own_tile;       // >= 0: symmetric mode, the members segment is only this tile (taken by split 0)
+    int filter;         // 0: every segment; 1: the members segment only; 2: the external segments only
 
     __device__ __forceinline__ void seek()
     {
         while (k < nseg) {
             const SegDesc sd = hd->seg[k];
+            const bool is_members = (sd.flags & kSegMembers) != 0;
+            if ((filter == 1 && !is_members) || (filter == 2 && is_members)) {
+                ++k;
+                continue;
+            }
             const int c = (sd.flags & kSegMembers) ? n_members : sd.count;
             const int per = (((c + S - 1) / S) + kTileJ - 1) / kTileJ * kTileJ;
             int a = s * per;
@@ -92,9 +98,10 @@ struct TileCursor {
         }
     }
     __device__ __forceinline__ void init(const HaloDesc *h, int S_, int s_, int n_members_, int parity_,
-                                         int own_tile_ = -1)
+                                         int own_tile_ = -1, int filter_ = 0)
     {
         own_tile = own_tile_;
+        filter = filter_;
         hd = h;
         nseg = h->nseg;
         k = 0;
@@ -107,6 +114,7 @@ struct TileCursor {
     __device__ __forceinline__ void init_range(int set_, int64_t begin, int count)
     {
         own_tile = -1;
+        filter = 0;
         hd = nullptr;
         nseg = 1;
         k = count > 0 ? 0 : 1;
@@ -219,7 +227,8 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
         t.s = 0;
         return true;
     }
-    if (!p.sym_enabled || groups < 2) return false;
+    // (a halo whose coming pass is incremental has none: loop_kernels.cu::k_schedule counts the same way)
+    if (!p.sym_enabled || groups < 2 || (p.incr_enabled && p.incr[t.h])) return false;
     // symmetric tickets: (row tile I, chunk c of the tiles J > I); ids of empty chunks are skipped
     local -= 3 * max(myblk, 0);
     const int ct = p.st->sym_chunk;
@@ -598,7 +607,9 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
     }
 }
 
-template <int T, int MINB, bool NP, bool SYM = false>
+// REUSE: the instantiations that know about the external-sum cache and the incremental passes; plans
+// without them run the REUSE = false kernels, whose code is what it was before those existed.
+template <int T, int MINB, bool NP, bool SYM = false, bool REUSE = false>
 __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const PotParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -613,6 +624,7 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
     rg.fill = rg.use = 0;
     float *col = reinterpret_cast<float *>(smem_raw + kWarpsPerBlock * kStages * (kStageFloats * 4 + 8)) + warp * kTileJ;
     static_assert(!SYM || (NP && T == 4), "symmetric tickets use 128-member tiles on the predicate-free kernel");
+    static_assert(!REUSE || NP, "cached and incremental sums live on the predicate-free path");
     if (lane == 0) {
         for (int i = 0; i < kStages; ++i) mbar_init(&rg.bars[i], 1);
         fence_mbar_init();
@@ -660,30 +672,57 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
             xi[t] = ok ? p.tx[tsel][tbase + i] : 0.f;
             yi[t] = ok ? p.ty[tsel][tbase + i] : 0.f;
             zi[t] = ok ? p.tz[tsel][tbase + i] : 0.f;
-            acc64[t] = 0.0;
         }
-        TileCursor cur;
-        cur.init(hd, tk.S, tk.s, tk.n_tgt, parity, SYM ? tk.group : -1);
-        if (NP) {
-            run_tiles<T, 1>(p, cur, rg, lane, tk.group * kGroup, tk.group * kGroup + kGroup, xi, yi, zi, acc64);
-            // zero separations outside the own tile (exact duplicates) or non-finite input:
-            // hand the halo to the predicated kernel
-            bool bad = false;
-#pragma unroll
-            for (int t = 0; t < T; ++t)
-                bad |= (tk.group * kGroup + t * 32 + lane < tk.n_tgt) && !(fabs(acc64[t]) <= 1.7976931348623157e308);
-            if (__any_sync(0xffffffffu, bad) && lane == 0) {
-                atomicExch(&p.halo_redo[tk.h], 1);
-                atomicExch(&p.st->redo_any, 1);
+        // Source phases of a main ticket.  Normally one: every segment of the halo.
+        // External cache: the members segment alone (filter 1) and, in the first pass only, the external
+        // segments on their own (filter 2) into phi_ext, which k_energy_flag adds in every later pass.
+        // Incremental pass: only the members the previous pass removed (k_energy_flag subtracts the sum
+        // from the self-term it kept); the externals are part of that kept sum or of phi_ext.
+        const bool incr = REUSE && p.incr_enabled && p.incr[tk.h];
+        int filt = 0, nphase = 1;
+        if (REUSE && p.cache_ext && hd->n_ext > 0 && !incr) {
+            if (st->pass == 0) {
+                filt = 1;
+                nphase = 2;
+            } else if (p.ext_ok[tk.h]) {
+                filt = 1;
             }
-        } else {
-            run_tiles<T, 0>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
         }
-        double *out = p.phi_part + static_cast<int64_t>(tk.s) * p.phi_stride + tbase;
+#pragma unroll 1
+        for (int ph = 0; ph < nphase; ++ph) {
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int i = tk.group * kGroup + t * 32 + lane;
-            if (i < tk.n_tgt) out[i] = acc64[t];
+            for (int t = 0; t < T; ++t) acc64[t] = 0.0;
+            TileCursor cur;
+            if (incr) {
+                const int nr = p.rem_cnt[tk.h];
+                const int per = (((nr + tk.S - 1) / tk.S) + kTileJ - 1) / kTileJ * kTileJ;
+                const int a = min(tk.s * per, nr), b = min(a + per, nr);
+                cur.init_range(6, hd->poff + a, b - a);
+            } else {
+                cur.init(hd, tk.S, tk.s, tk.n_tgt, parity, SYM ? tk.group : -1, filt + ph);
+            }
+            if (NP) {
+                run_tiles<T, 1>(p, cur, rg, lane, tk.group * kGroup, tk.group * kGroup + kGroup, xi, yi, zi, acc64);
+                // zero separations outside the own tile (exact duplicates) or non-finite input:
+                // hand the halo to the predicated kernel
+                bool bad = false;
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    bad |= (tk.group * kGroup + t * 32 + lane < tk.n_tgt) && !(fabs(acc64[t]) <= 1.7976931348623157e308);
+                if (__any_sync(0xffffffffu, bad) && lane == 0) {
+                    atomicExch(&p.halo_redo[tk.h], 1);
+                    atomicExch(&p.st->redo_any, 1);
+                }
+            } else {
+                run_tiles<T, 0>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
+            }
+            // (the first pass works on the uncompacted buffer, so tbase + i is the member's original slot)
+            double *out = (ph == 0 ? p.phi_part : p.phi_ext) + static_cast<int64_t>(tk.s) * p.phi_stride + tbase;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int i = tk.group * kGroup + t * 32 + lane;
+                if (i < tk.n_tgt) out[i] = acc64[t];
+            }
         }
     }
 }
@@ -901,9 +940,11 @@ struct FastVariant {
     int targets, min_blocks;
     void (*pred)(const PotParams);
     void (*np)(const PotParams);
+    void (*np_reuse)(const PotParams);      // external-sum cache / incremental passes
 };
 
-#define HALMA_VARIANT(T, B) {T, B, k_potential_fast<T, B, false>, k_potential_fast<T, B, true>}
+#define HALMA_VARIANT(T, B) \
+    {T, B, k_potential_fast<T, B, false>, k_potential_fast<T, B, true>, k_potential_fast<T, B, true, false, true>}
 const FastVariant kVariants[] = {
     HALMA_VARIANT(4, 6), HALMA_VARIANT(1, 8), HALMA_VARIANT(2, 8), HALMA_VARIANT(4, 4),
     HALMA_VARIANT(3, 6), HALMA_VARIANT(6, 3), HALMA_VARIANT(8, 3),
@@ -916,6 +957,8 @@ constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 typedef void (*SymKernel)(const PotParams);
 const SymKernel kSymKernels[3] = {k_potential_fast<4, 4, true, true>, k_potential_fast<4, 5, true, true>,
                                   k_potential_fast<4, 6, true, true>};
+const SymKernel kSymReuseKernels[3] = {k_potential_fast<4, 4, true, true, true>, k_potential_fast<4, 5, true, true, true>,
+                                       k_potential_fast<4, 6, true, true, true>};
 int sym_choice()
 {
     static int c = [] {
@@ -926,8 +969,9 @@ int sym_choice()
     return c;
 }
 #define kSymKernel kSymKernels[sym_choice()]
+#define kSymReuseKernel kSymReuseKernels[sym_choice()]
 int g_bps[16] = {0};
-int g_sym_bps = 0;
+int g_sym_bps = 0, g_sym_reuse_bps = 0;
 
 int forced_variant()
 {
@@ -981,12 +1025,23 @@ cudaError_t potential_configure(int mode, int variant, int *blocks_per_sm)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, v.pred, kPotentialBlock, kSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, v.np, kPotentialBlock, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    // the reuse kernels are launched with the same grid: they are held to the same minimum residency
+    e = cudaFuncSetAttribute(v.np_reuse, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    int c = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, v.np_reuse, kPotentialBlock, kSmemBytes);
+    b = b < c ? b : c;
     *blocks_per_sm = a < b ? a : b;
     if (variant < 16) g_bps[variant] = *blocks_per_sm;
     if (e == cudaSuccess && variant == 0) {
         e = cudaFuncSetAttribute(kSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sym_bps, kSymKernel, kPotentialBlock, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kSymReuseKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sym_reuse_bps, kSymReuseKernel, kPotentialBlock, kSmemBytes);
     }
     return e;
 }
@@ -997,8 +1052,14 @@ cudaError_t potential_launch(const PotParams &p, int mode, int variant, int grid
         k_potential_exact<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else if (p.np_enabled && !p.redo_only && p.sym_enabled) {
         const int per_sm = variant < 16 && g_bps[variant] > 0 ? g_bps[variant] : 1;
-        kSymKernel<<<grid_blocks / per_sm * (g_sym_bps > 0 ? g_sym_bps : 1), kPotentialBlock, kSmemBytes, stream>>>(p);
-    } else if (p.np_enabled && !p.redo_only)
+        if (p.cache_ext || p.incr_enabled)
+            kSymReuseKernel<<<grid_blocks / per_sm * (g_sym_reuse_bps > 0 ? g_sym_reuse_bps : 1), kPotentialBlock,
+                              kSmemBytes, stream>>>(p);
+        else
+            kSymKernel<<<grid_blocks / per_sm * (g_sym_bps > 0 ? g_sym_bps : 1), kPotentialBlock, kSmemBytes, stream>>>(p);
+    } else if (p.np_enabled && !p.redo_only && (p.cache_ext || p.incr_enabled))
+        kVariants[variant].np_reuse<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
+    else if (p.np_enabled && !p.redo_only)
         kVariants[variant].np<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else
         kVariants[variant].pred<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);

@@ -136,6 +136,14 @@ class UnbindResult:
     stats: Optional[RunStats] = field(default=None, repr=False)
 
 
+REUSE_DEFAULT = "0"
+
+
+def _reuse_default(name: str) -> bool:
+    import os
+    return os.environ.get(name, REUSE_DEFAULT) not in ("0", "")
+
+
 class UnbindPlan:
     """A batch of haloes resident on one GPU.
 
@@ -144,12 +152,19 @@ class UnbindPlan:
     Stellar layout (halo_properties.py:333-339): split_classes=False, groups[:n_pre] are
     summed before the members (gas), the rest after (DM).  Gas layout (halo_gas.py:301-450):
     split_classes=True, members (gas) first, then each group as its own float32 class.
+
+    cache_external / incremental (FAST mode, plans on the predicate-free path, one GPU): do not repeat
+    work whose result cannot have changed -- the sum over the fixed external sources is evaluated by the
+    first pass only, and after a pass that removed at most a third of a halo's members the next pass
+    evaluates survivors x removed and subtracts (see include/halma_unbind.h).  None: HALMA_CACHE_EXT /
+    HALMA_INCREMENTAL.
     """
 
     def __init__(self, offsets, ext_offsets: Sequence = (), *, mode="fast", n_pre: int = 0,
                  split_classes: bool = False, vb_fixed: bool = False, max_iter: int = 64,
                  G: float = G_CONST, kappa: float = 9.0, device: int = 0, rank: int = 0, n_ranks: int = 1,
-                 use_graph: Optional[bool] = None, symmetric: Optional[bool] = None):
+                 use_graph: Optional[bool] = None, symmetric: Optional[bool] = None,
+                 cache_external: Optional[bool] = None, incremental: Optional[bool] = None):
         L = _lib.lib()
         self._L = L
         self.offsets = _i64(offsets)
@@ -184,6 +199,9 @@ class UnbindPlan:
             import os
             symmetric = os.environ.get("HALMA_SYMMETRIC", "1") not in ("0", "")      # on unless HALMA_SYMMETRIC=0
         cfg.symmetric = int(bool(symmetric))
+        # work the loop does not repeat (halma_unbind_config.cache_external / .incremental)
+        cfg.cache_external = int(_reuse_default("HALMA_CACHE_EXT") if cache_external is None else bool(cache_external))
+        cfg.incremental = int(_reuse_default("HALMA_INCREMENTAL") if incremental is None else bool(incremental))
         self.cfg = cfg
         ptrs = (C.POINTER(C.c_int64) * max(1, len(self.ext_offsets)))()
         for g, e in enumerate(self.ext_offsets):
@@ -334,7 +352,8 @@ def nccl_unique_id() -> bytes:
 def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (), n_pre: int = 0,
                      split_classes: bool = False, vb=None, kappa: float = 9.0, max_iter: int = 64,
                      mode="fast", device: int = 0, G: float = G_CONST, temp=None,
-                     cold_T: float = 5 * 1e4, symmetric: Optional[bool] = None, streams: int = 1) -> CatalogueResult:
+                     cold_T: float = 5 * 1e4, symmetric: Optional[bool] = None, streams: int = 1,
+                     cache_external: Optional[bool] = None, incremental: Optional[bool] = None) -> CatalogueResult:
     """Unbind every halo of a catalogue in one batched, device-resident run.
 
     groups: sequence of (ext_offsets, mass, x, y, z) external source groups.
@@ -350,10 +369,11 @@ def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (
     offsets = _i64(offsets)
     if streams > 1 and len(offsets) - 1 >= 2 * streams:
         return _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, split_classes, vb, kappa,
-                                       max_iter, mode, device, G, temp, cold_T, symmetric, streams)
+                                       max_iter, mode, device, G, temp, cold_T, symmetric, streams,
+                                       cache_external, incremental)
     plan = UnbindPlan(offsets, [g[0] for g in groups], mode=mode, n_pre=n_pre, split_classes=split_classes,
                       vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa, device=device,
-                      symmetric=symmetric)
+                      symmetric=symmetric, cache_external=cache_external, incremental=incremental)
     try:
         plan.upload_members(x, y, z, vx, vy, vz, mass)
         for k, g in enumerate(groups):
@@ -383,7 +403,8 @@ def cost_cuts(offsets, ext_offsets, parts: int) -> list:
 
 
 def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, split_classes, vb, kappa, max_iter,
-                            mode, device, G, temp, cold_T, symmetric, streams) -> CatalogueResult:
+                            mode, device, G, temp, cold_T, symmetric, streams, cache_external=None,
+                            incremental=None) -> CatalogueResult:
     import threading
     nh = len(offsets) - 1
     n = int(offsets[-1])
@@ -407,7 +428,8 @@ def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, s
             sub = [(g[0][a:b + 1] - g[0][a],) + tuple(arr[int(g[0][a]):int(g[0][b])] for arr in g[1:]) for g in groups]
             with UnbindPlan(offsets[a:b + 1] - o0, [g[0] for g in sub], mode=mode, n_pre=n_pre,
                             split_classes=split_classes, vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa,
-                            device=device, symmetric=symmetric) as plan:
+                            device=device, symmetric=symmetric, cache_external=cache_external,
+                            incremental=incremental) as plan:
                 plan.upload_members(*[m[o0:o1] for m in members])
                 for gi, g in enumerate(sub):
                     plan.upload_group(gi, g[1], g[2], g[3], g[4])
@@ -438,7 +460,8 @@ def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, s
 
 def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence = (),
                 split_classes: bool = False, kappa: float = 9.0, vb_fixed=None, max_iter: int = 64,
-                mode="fast", device: int = 0, G: float = G_CONST, symmetric: Optional[bool] = None) -> UnbindResult:
+                mode="fast", device: int = 0, G: float = G_CONST, symmetric: Optional[bool] = None,
+                cache_external: Optional[bool] = None, incremental: Optional[bool] = None) -> UnbindResult:
     """One halo.  pre / post: sequences of (mass, x, y, z) fixed source groups summed before /
     after the members (same keywords as oracle.unbind_halo)."""
     n = len(x)
@@ -447,7 +470,8 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence
     res = unbind_catalogue(np.array([0, n], np.int64), x, y, z, vx, vy, vz, mass, groups=groups,
                            n_pre=len(pre), split_classes=split_classes,
                            vb=None if vb_fixed is None else np.asarray(vb_fixed, np.float64).reshape(1, 3),
-                           kappa=kappa, max_iter=max_iter, mode=mode, device=device, G=G, symmetric=symmetric)
+                           kappa=kappa, max_iter=max_iter, mode=mode, device=device, G=G, symmetric=symmetric,
+                           cache_external=cache_external, incremental=incremental)
     h = res.halos[0]
     return UnbindResult(res.mask.astype(bool), res.members(0).astype(np.int64), res.be32, res.energy, h.n_iter,
                         h.mass, h.com, h.vb, h.pairs, h.converged, res.stats)

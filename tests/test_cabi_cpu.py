@@ -27,10 +27,20 @@ def test_header_symbols_are_exported():
     assert set(names) == set(_lib.EXPORTS)
 
 
-def test_struct_sizes_match_header():
-    assert ctypes.sizeof(_lib.UnbindConfig) == 64
+def test_struct_sizes_match_header(tmp_path):
+    assert ctypes.sizeof(_lib.UnbindConfig) == 72
     assert ctypes.sizeof(_lib.HaloResult) == 120
     assert ctypes.sizeof(_lib.RunStats) == 48
+    # the same numbers from the header itself, through the C compiler
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "halma_unbind.h"\nint main(void){printf("%zu %zu %zu\\n", '
+                   'sizeof(halma_unbind_config), sizeof(halma_halo_result), sizeof(halma_run_stats));return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(v) for v in out] == [ctypes.sizeof(_lib.UnbindConfig), ctypes.sizeof(_lib.HaloResult),
+                                     ctypes.sizeof(_lib.RunStats)]
 
 
 def test_abi_version():
