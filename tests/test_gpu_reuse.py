@@ -15,6 +15,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+from oracle import reuse_model as RM
 from pyhalma_b200 import synth
 from pyhalma_b200.unbind import UnbindPlan, unbind_catalogue, unbind_halo
 
@@ -60,6 +61,9 @@ def test_stellar_halo_with_externals(symmetric):
         r = unbind_halo(*args, mode="fast", symmetric=symmetric, **v, **kw)
         # cached externals are evaluated once: at least (passes - 1) x (bound members) x n_ext fewer evaluations
         check_against(r, ref, o, 9.0, (o.n_iter - 1) * int(o.mask.sum()) * n_ext if v["cache_external"] else 1)
+        if np.array_equal(r.mask, o.mask):
+            # exactly the passes the numpy model of the bookkeeping takes (oracle/reuse_model.py)
+            assert r.stats.evaluations == RM.expected_evaluations(o.n_bound_history, n_ext, symmetric=symmetric, **v)
         again = unbind_halo(*args, mode="fast", symmetric=symmetric, **v, **kw)
         assert np.array_equal(again.be32.view(np.uint32), r.be32.view(np.uint32))      # bit-reproducible
         assert np.array_equal(again.mask, r.mask) and np.array_equal(again.energy, r.energy)
@@ -80,6 +84,8 @@ def test_gas_layout_lattice_with_fixed_bulk_velocity():
     for v in VARIANTS:
         r = unbind_halo(*args, mode="fast", **v, **kw)
         check_against(r, ref, o, 2.0, 1 if v["cache_external"] else 0)
+        if np.array_equal(r.mask, o.mask):
+            assert r.stats.evaluations == RM.expected_evaluations(o.n_bound_history, len(d) + len(s), symmetric=True, **v)
         # potentials of the particles removed in earlier passes are the ones of the pass that removed them
         gone = ~o.mask & (o.be32 > 0)
         if gone.any():
