@@ -142,8 +142,8 @@ typedef struct halma_unbind_config {
                                 during the loop, so the sum over them is evaluated by the first pass only,
                                 kept per member in float64 and added in every later pass.  Same terms, same
                                 tolerances; halma_run_stats.evaluations counts what was actually evaluated. */
-    int32_t incremental;     /* 1 (same conditions): when a pass removed at most a third of a halo's members,
-                                the next pass of that halo only evaluates survivors x removed members and
+    int32_t incremental;     /* 1 (FAST mode, predicate-free path; also in split mode): when a pass removed at
+                                most a third of a halo's members, the next pass of that halo only evaluates survivors x removed members and
                                 subtracts that from the predicate-free sum kept from the pass before (the
                                 same per-pair terms; the difference is float32 partial-sum rounding,
                                 ~1e-7 of the removed contribution).  A pass that fell back to the predicated

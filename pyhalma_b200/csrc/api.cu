@@ -831,10 +831,12 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.sym_ext = P->d_symq.p;
     L.sym_q = P->sym ? P->d_symq.p + nh : nullptr;
     // External-sum cache and incremental passes ride on the predicate-free path (whose sums are kept per
-    // member in float64 and whose excluded pairs are handled by the correction tickets every pass).  Not in
-    // split mode: the kept sums would need their own all-reduce.
+    // member in float64 and whose excluded pairs are handled by the correction tickets every pass).
+    // Split mode: incremental passes need nothing extra -- their main tickets are dealt to the ranks and
+    // all-reduced like any others and kernels 2-3, which keep the sums, run replicated; the external-sum
+    // planes would need an all-reduce of their own in the first pass, so the cache stays off there.
     P->cache_ext = cfg.cache_external && P->np && cfg.n_ranks == 1 && P->max_ext > 0;
-    P->incr = cfg.incremental && P->np && cfg.n_ranks == 1;
+    P->incr = cfg.incremental && P->np;
     if (P->cache_ext || P->incr) CU_TRY(P->d_reuse_int.alloc(3 * std::max<size_t>(nh, 1)));
     if (P->cache_ext) CU_TRY(P->d_phi_ext.alloc(planes * NP));
     if (P->incr) {

@@ -39,6 +39,11 @@
 // FAST, symmetric self-term ("SYM", on top of NP)  a pair of MEMBERS in different 128-member tiles
 //        is evaluated once and feeds both particles (sym_ticket below): half the MUFU.RSQ work of
 //        the member x member term, exact and therefore order-independent float64 accumulation.
+//
+// REUSE (the <..., REUSE = true> instantiations; halma_unbind_config.cache_external / .incremental)  the same
+//        main tickets with a choice of WHICH sources they stream: the members only once the externals' sum
+//        is cached (first pass: members, then the externals into their own planes), or only the members
+//        the previous pass removed (incremental pass; loop_kernels.cu keeps the per-member sums).
 #include <cstdlib>
 
 #include "halma_common.cuh"

@@ -136,7 +136,7 @@ class UnbindResult:
     stats: Optional[RunStats] = field(default=None, repr=False)
 
 
-REUSE_DEFAULT = "0"
+REUSE_DEFAULT = "1"          # on unless HALMA_CACHE_EXT=0 / HALMA_INCREMENTAL=0
 
 
 def _reuse_default(name: str) -> bool:

@@ -1,7 +1,7 @@
 """Split mode (one halo shared by all ranks, one NCCL all-reduce per pass) against the
 single-GPU run of the same halo: results must be bit-identical (with the same settings: the
-external-sum cache and the incremental passes are single-GPU features, so the reference run has
-them off).
+external-sum cache is a single-GPU feature, so the reference run has it off; incremental passes
+run in both).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 scripts/split_check.py
@@ -41,7 +41,7 @@ for mode, n_star, n_gas in (("exact", 6000, 3000), ("fast", 30000, 20000), ("fas
         st = plan.run()
         res = plan.download()
     single = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, pre=[g.pos_mass()], post=[d.pos_mass()],
-                         kappa=9.0, mode=mode, device=local, cache_external=False, incremental=False)
+                         kappa=9.0, mode=mode, device=local, cache_external=False)
     same = (np.array_equal(res.mask.astype(bool), single.mask)
             and np.array_equal(res.be32.view(np.uint32), single.be32.view(np.uint32))
             and np.array_equal(res.energy, single.energy) and res.halos[0].n_iter == single.n_iter
@@ -71,7 +71,7 @@ with UnbindPlan(off, eoff, mode="fast", split_classes=True, vb_fixed=True, kappa
     st = plan.run()
     res = plan.download()
 single = unbind_halo(g.x, g.y, g.z, g.vx, g.vy, g.vz, g.mass, post=[d.pos_mass(), s.pos_mass()], split_classes=True,
-                     kappa=2.0, vb_fixed=vb, mode="fast", device=local, cache_external=False, incremental=False)
+                     kappa=2.0, vb_fixed=vb, mode="fast", device=local, cache_external=False)
 same = (np.array_equal(res.mask.astype(bool), single.mask) and np.array_equal(res.be32.view(np.uint32), single.be32.view(np.uint32))
         and np.array_equal(res.energy, single.energy) and res.halos[0].n_iter == single.n_iter)
 flag = torch.tensor([1 if same else 0], device="cuda")
