@@ -6,11 +6,12 @@ SURVEY.md §3.4:
 
 * the sum over the fixed external sources is evaluated by the first pass only;
 * after a pass that removed at most a third of a halo's members (2 * n_removed <= n_left) the next
-  pass evaluates survivors x removed members and subtracts that from the sum it kept.
+  pass evaluates survivors x removed members -- with the reference's predicate
+  (fortran_modules/particle_subroutines.f90:499-501: a pair counts only if all three coordinates
+  differ) -- and subtracts that from the complete potential it kept.
 
-Both work on the PREDICATE-FREE sum (every pair with r > 0); the pairs the reference excludes
-(fortran_modules/particle_subroutines.f90:499-501: any coordinate equal) are subtracted every pass
-from the current sources, like the correction tickets of the CUDA kernel do.
+A full pass works on the PREDICATE-FREE sum (every pair with r > 0) and subtracts the pairs the
+reference excludes from the current sources, like the correction tickets of the CUDA kernel do.
 
 This model restates that bookkeeping with the FAST kernel's arithmetic granularity -- float32 terms,
 float32 partial sums over 32 sources, float64 accumulation -- so that the CPU suite can pin (a) that
@@ -41,12 +42,13 @@ def _terms(tx, ty, tz, sm, sx, sy, sz):
     return t, r2, (dx == 0), (dy == 0), (dz == 0)
 
 
-def _free_sum(tx, ty, tz, sm, sx, sy, sz):
-    """Predicate-free sum (pairs with r > 0), float32 partials over CHUNK sources, float64 total."""
+def _free_sum(tx, ty, tz, sm, sx, sy, sz, predicate: bool = False):
+    """Predicate-free sum (pairs with r > 0) or, with predicate=True, the reference's sum (pairs whose three
+    coordinates all differ); float32 partials over CHUNK sources, float64 total."""
     out = np.zeros(len(tx), np.float64)
     for a in range(0, len(sm), CHUNK):
-        t, r2, _, _, _ = _terms(tx, ty, tz, sm[a:a + CHUNK], sx[a:a + CHUNK], sy[a:a + CHUNK], sz[a:a + CHUNK])
-        t = np.where(r2 > 0, t, np.float32(0))
+        t, r2, ex, ey, ez = _terms(tx, ty, tz, sm[a:a + CHUNK], sx[a:a + CHUNK], sy[a:a + CHUNK], sz[a:a + CHUNK])
+        t = np.where(~(ex | ey | ez) if predicate else (r2 > 0), t, np.float32(0))
         part = np.zeros(len(tx), np.float32)
         for k in range(t.shape[1]):
             part = part + t[:, k]
@@ -89,7 +91,7 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, ext: Sequence = (), kappa: float =
     n_ext = len(em)
     N = len(X)
     idx = np.arange(N)
-    phi_self = np.zeros(N)
+    phi_keep = np.zeros(N)          # the complete float64 potential of the previous pass
     phi_ext = np.zeros(N)
     be_out = np.zeros(N, f32)
     e_out = np.zeros(N)
@@ -103,11 +105,11 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, ext: Sequence = (), kappa: float =
         n = len(idx)
         if incr_next:
             r = removed
-            phi_self[idx] -= _free_sum(*t, M[r], X[r], Y[r], Z[r])
+            phi = phi_keep[idx] - _free_sum(*t, M[r], X[r], Y[r], Z[r], predicate=True)
             evals += n * len(r)
             kinds.append("incr")
         else:
-            s = _free_sum(*t, M[idx], X[idx], Y[idx], Z[idx])
+            phi = _free_sum(*t, M[idx], X[idx], Y[idx], Z[idx])
             evals += n * n
             cached = cache_external and it > 0
             if n_ext and not cached:
@@ -116,12 +118,14 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, ext: Sequence = (), kappa: float =
                 if cache_external:
                     phi_ext[idx] = e
                 else:
-                    s = s + e
-            phi_self[idx] = s
+                    phi = phi + e
+            if cache_external:
+                phi = phi + phi_ext[idx]
+            src = (np.concatenate((M[idx], em)), np.concatenate((X[idx], ex)), np.concatenate((Y[idx], ey)),
+                   np.concatenate((Z[idx], ez)))
+            phi = phi - _excluded_sum(*t, *src)
             kinds.append("full")
-        src = (np.concatenate((M[idx], em)), np.concatenate((X[idx], ex)), np.concatenate((Y[idx], ey)),
-               np.concatenate((Z[idx], ez)))
-        phi = phi_self[idx] + (phi_ext[idx] if cache_external else 0.0) - _excluded_sum(*t, *src)
+        phi_keep[idx] = phi
         be = phi.astype(f32)
         if vb_fixed is None:
             Mtot = O.total_mass(idx, m64)

@@ -478,7 +478,7 @@ struct halma_plan {
     bool sym = false;
     // external-sum cache and incremental passes (FAST predicate-free path, one GPU)
     bool cache_ext = false, incr = false;
-    DBuf<double> d_phi_ext, d_phi_self;
+    DBuf<double> d_phi_ext, d_phi_keep;
     DBuf<float> d_rem;                    // 4 * n_pad: members removed by the last pass (x y z m)
     DBuf<int32_t> d_reuse_int;            // ext_ok, incr, rem_cnt: 3 * n_halo
     DBuf<int32_t> d_cint;                 // per-chunk ints: cnt, off
@@ -532,7 +532,7 @@ struct halma_plan {
         d_src_halo.release(); d_sslot.release(); d_stgt.release(); d_sinv.release(); d_redo.release();
         d_nsel.release(); d_keys.release(); d_ids.release(); d_skey.release(); d_ismem.release();
         d_sorttemp.release(); d_sf.release(); d_corr.release();
-        d_phi_ext.release(); d_phi_self.release(); d_rem.release(); d_reuse_int.release();
+        d_phi_ext.release(); d_phi_keep.release(); d_rem.release(); d_reuse_int.release();
     }
     ~halma_plan()
     {
@@ -840,13 +840,13 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     if (P->cache_ext || P->incr) CU_TRY(P->d_reuse_int.alloc(3 * std::max<size_t>(nh, 1)));
     if (P->cache_ext) CU_TRY(P->d_phi_ext.alloc(planes * NP));
     if (P->incr) {
-        CU_TRY(P->d_phi_self.alloc(NP));
+        CU_TRY(P->d_phi_keep.alloc(NP));
         CU_TRY(P->d_rem.alloc(4 * NP));
     }
     L.phi_ext = P->d_phi_ext.p;
     L.ext_ok = P->d_reuse_int.p;
     L.cache_ext = P->cache_ext ? 1 : 0;
-    L.phi_self = P->d_phi_self.p;
+    L.phi_keep = P->d_phi_keep.p;
     L.rx = P->d_rem.p;
     L.ry = P->incr ? P->d_rem.p + NP : nullptr;
     L.rz = P->incr ? P->d_rem.p + 2 * NP : nullptr;

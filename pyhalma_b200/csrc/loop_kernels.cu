@@ -219,26 +219,28 @@ __global__ void __launch_bounds__(kCh) k_energy_flag(const LoopParams p)
             const bool redo = p.np_enabled && p.halo_redo[h];
             const bool inc = p.incr_enabled && p.incr[h];
             const int64_t slot = hd.poff + (g - hd.uoff);      // the member's original slot
-            if (p.sym_enabled && !redo && !inc) phi += p.phi_sym[i];
-            if (p.incr_enabled && !redo) {
-                // incremental pass: the planes hold the sum over the members the previous pass removed;
-                // take it out of the predicate-free sum kept from that pass
-                if (inc) phi = p.phi_self[slot] - phi;
-                p.phi_self[slot] = phi;
-            }
-            if (p.cache_ext && hd.n_ext > 0 && !redo && p.ext_ok[h]) {
-                // sum over the external sources, evaluated by the first pass only (potential.cu)
-                if (p.st->pass == 0) {
-                    double e = p.phi_ext[slot];
-                    for (int k = 1; k < S; ++k) e += p.phi_ext[static_cast<int64_t>(k) * p.n_pad + slot];
-                    p.phi_ext[slot] = e;
+            if (inc && !redo) {
+                // incremental pass: the planes hold what the members removed by the previous pass contributed
+                // (reference predicate applied); take it out of the potential kept from that pass
+                phi = p.phi_keep[slot] - phi;
+            } else if (!redo) {
+                if (p.sym_enabled) phi += p.phi_sym[i];
+                if (p.cache_ext && hd.n_ext > 0 && p.ext_ok[h]) {
+                    // sum over the external sources, evaluated by the first pass only (potential.cu)
+                    if (p.st->pass == 0) {
+                        double e = p.phi_ext[slot];
+                        for (int k = 1; k < S; ++k) e += p.phi_ext[static_cast<int64_t>(k) * p.n_pad + slot];
+                        p.phi_ext[slot] = e;
+                    }
+                    phi += p.phi_ext[slot];
                 }
-                phi += p.phi_ext[slot];
+                if (p.np_enabled) {
+                    // predicate-free path: take out the pairs that share a coordinate (potential.cu)
+                    phi -= (p.ax[0].corr[slot] + p.ax[1].corr[slot]) + p.ax[2].corr[slot];
+                }
             }
-            if (p.np_enabled && !redo) {
-                // predicate-free path: take out the pairs that share a coordinate (potential.cu)
-                phi -= (p.ax[0].corr[slot] + p.ax[1].corr[slot]) + p.ax[2].corr[slot];
-            }
+            // the complete float64 potential, kept for a following incremental pass
+            if (p.incr_enabled && !redo) p.phi_keep[slot] = phi;
             const float be = __double2float_rn(phi);
             // halo_properties.py:342-351 / halo_gas.py:456-465: float32 chain, two roundings
             float pe = -be;
@@ -444,9 +446,9 @@ __global__ void __launch_bounds__(kCh) k_halo_decide(const LoopParams p, int ini
                 // a first pass that fell back to the predicated kernel leaves no usable external sums
                 if (p.cache_ext && p.st->pass == 0 && redo) p.ext_ok[h] = 0;
                 if (p.incr_enabled) {
-                    // The coming pass is incremental when this one left a valid predicate-free sum behind
-                    // (k_energy_flag, phi_self) and removed at most a third of the members: survivors x removed
-                    // is then cheaper than a full pass even with the symmetric self-term.
+                    // The coming pass is incremental when this one left a valid potential behind (k_energy_flag,
+                    // phi_keep) and removed at most a third of the members: survivors x removed is then cheaper
+                    // than a full pass even with the symmetric self-term.
                     const int n_rem = n_old - n_new;
                     p.rem_cnt[h] = n_rem;
                     p.incr[h] = (!redo && n_rem > 0 && 2ll * n_rem <= n_new) ? 1 : 0;
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const LoopParams p, int init)
                 max_split = max(max_split, S);
                 items = my_groups(n, p.group_size, p.rank, p.n_ranks) * S;
                 // correction tickets: three axes x blocks of the (static) sorted member list
-                if (p.np_enabled) items += 3 * my_groups(p.halo[h].n0, p.group_size, p.rank, p.n_ranks);
+                if (p.np_enabled && !inc) items += 3 * my_groups(p.halo[h].n0, p.group_size, p.rank, p.n_ranks);
                 // symmetric tickets: row tiles x chunks of column tiles (potential.cu::decode_ticket)
                 if (p.sym_enabled && !inc) {
                     const int tiles = (n + p.group_size - 1) / p.group_size;

@@ -62,8 +62,8 @@ struct LoopParams {
     double *phi_ext;                      // [max_split][n_pad] by original slot; plane 0 holds the folded sum
     int32_t *ext_ok;                      // [n_halo] 1: phi_ext of this halo is valid
     int32_t cache_ext;
-    // incremental passes: kept predicate-free self-term, members removed by the previous pass
-    double *phi_self;                     // [n_pad] by original slot
+    // incremental passes: the complete float64 potential of the previous pass, members it removed
+    double *phi_keep;                     // [n_pad] by original slot
     float *rx, *ry, *rz, *rm;             // [n_pad] removed members of the last pass, per halo at poff
     int32_t *rem_cnt;                     // [n_halo]
     int32_t *incr;                        // [n_halo] the coming / current pass of the halo is incremental

@@ -222,6 +222,9 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
         return true;
     }
     if (!p.np_enabled) return false;
+    // a halo whose coming pass is incremental has main tickets only: they apply the reference's predicate to
+    // the few removed members themselves (loop_kernels.cu::k_schedule counts the same way)
+    if (p.incr_enabled && p.incr[t.h]) return false;
     local -= n_main;
     // correction blocks are dealt round-robin to the ranks like the target groups
     const int nblk = (p.halo[t.h].n0 + kGroup - 1) / kGroup;
@@ -232,8 +235,7 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
         t.s = 0;
         return true;
     }
-    // (a halo whose coming pass is incremental has none: loop_kernels.cu::k_schedule counts the same way)
-    if (!p.sym_enabled || groups < 2 || (p.incr_enabled && p.incr[t.h])) return false;
+    if (!p.sym_enabled || groups < 2) return false;
     // symmetric tickets: (row tile I, chunk c of the tiles J > I); ids of empty chunks are skipped
     local -= 3 * max(myblk, 0);
     const int ct = p.st->sym_chunk;
@@ -681,8 +683,9 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
         // Source phases of a main ticket.  Normally one: every segment of the halo.
         // External cache: the members segment alone (filter 1) and, in the first pass only, the external
         // segments on their own (filter 2) into phi_ext, which k_energy_flag adds in every later pass.
-        // Incremental pass: only the members the previous pass removed (k_energy_flag subtracts the sum
-        // from the self-term it kept); the externals are part of that kept sum or of phi_ext.
+        // Incremental pass: only the members the previous pass removed, WITH the reference's predicate, so the
+        // sum is exactly what those members contributed to the potential k_energy_flag kept from the previous
+        // pass (externals and corrections included) and no correction ticket is needed.
         const bool incr = REUSE && p.incr_enabled && p.incr[tk.h];
         int filt = 0, nphase = 1;
         if (REUSE && p.cache_ext && hd->n_ext > 0 && !incr) {
@@ -706,8 +709,13 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
             } else {
                 cur.init(hd, tk.S, tk.s, tk.n_tgt, parity, SYM ? tk.group : -1, filt + ph);
             }
-            if (NP) {
+            if (REUSE && incr)
+                run_tiles<T, 0>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
+            else if (NP)
                 run_tiles<T, 1>(p, cur, rg, lane, tk.group * kGroup, tk.group * kGroup + kGroup, xi, yi, zi, acc64);
+            else
+                run_tiles<T, 0>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
+            if (NP) {
                 // zero separations outside the own tile (exact duplicates) or non-finite input:
                 // hand the halo to the predicated kernel
                 bool bad = false;
@@ -718,8 +726,6 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
                     atomicExch(&p.halo_redo[tk.h], 1);
                     atomicExch(&p.st->redo_any, 1);
                 }
-            } else {
-                run_tiles<T, 0>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
             }
             // (the first pass works on the uncompacted buffer, so tbase + i is the member's original slot)
             double *out = (ph == 0 ? p.phi_part : p.phi_ext) + static_cast<int64_t>(tk.s) * p.phi_stride + tbase;
