@@ -319,6 +319,13 @@ static int potential_dev(DeviceCtx *c, int mode, const float *sm, const float *s
     return HALMA_OK;
 }
 
+// halma_potential_f32 for large FAST calls, defined after the plan API below.
+constexpr int kPlanPathDeclined = 1;
+static bool potential_plan_worthwhile(int64_t n_src, int64_t n_tgt);
+static int potential_via_plan(int device, const float *sm, const float *sx, const float *sy, const float *sz,
+                              int64_t n_src, const float *tx, const float *ty, const float *tz, int64_t n_tgt,
+                              float *out_be);
+
 static int check_mode(int mode)
 {
     if (mode != HALMA_MODE_FAST && mode != HALMA_MODE_EXACT) return fail(HALMA_ERR_INVALID, "unknown mode");
@@ -357,6 +364,11 @@ extern "C" int halma_potential_f32(int device, int mode, const float *src_m, con
     if (n_src > 0 && (!src_m || !src_x || !src_y || !src_z)) return fail(HALMA_ERR_INVALID, "null source pointer");
     DeviceCtx *c;
     if (int rc = get_ctx(device, &c)) return rc;
+    if (mode == HALMA_MODE_FAST && potential_plan_worthwhile(n_src, n_tgt)) {
+        // large call: the predicate-free kernel (and, for a self call, the symmetric self-term) of the plans
+        const int rc = potential_via_plan(device, src_m, src_x, src_y, src_z, n_src, tgt_x, tgt_y, tgt_z, n_tgt, out_be);
+        if (rc != kPlanPathDeclined) return rc;
+    }
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t sb = up256((n_src + 4) * sizeof(float)), tb = up256((n_tgt + 4) * sizeof(float));
     const size_t wb = up256(static_cast<size_t>(halma_potential_workspace_bytes(n_src, n_tgt)));
@@ -1392,4 +1404,153 @@ extern "C" int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n, cons
     if (!rc) rc = halma_plan_download(P, mask, be, energy, idx, result);
     halma_plan_destroy(P);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// brute_force_binding_energy through a one-pass plan (large FAST calls of halma_potential_f32; opt-in with
+// HALMA_POT_PLAN_MIN_PAIRS=<pairs>, e.g. 1e10).
+//
+// The direct path (potential_dev) runs the predicated kernel.  For a large call it pays to build the sorted
+// source copies once and use the predicate-free kernel + correction tickets of the plans, and where targets
+// are also sources the symmetric self-term on top.  The reference's callers come in three shapes:
+//   * the targets ARE the sources (gas-gas of RPS, halo_gas.py:306-328; stars-stars of most_bound_particle,
+//     :602-622);
+//   * the targets are a block of the sources (escape_velocity_unbinding_fortran, halo_properties.py:333-339:
+//     sources = concat(gas, stars, DM), targets = the stars);
+//   * the targets are other particles (DM -> gas, stars -> gas).
+// In the first two the block becomes the plan's members and the sources before / after it external groups; in
+// the third the targets are massless members that are left out of the source list (PotParams::ext_only) and the
+// sources one external group.  One pass, fixed zero bulk velocity: out_be is the plan's `be`.
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void k_widen_members(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                                const float *__restrict__ m, int64_t n, double *__restrict__ out7)
+{
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        out7[i] = static_cast<double>(x[i]);
+        out7[n + i] = static_cast<double>(y[i]);
+        out7[2 * n + i] = static_cast<double>(z[i]);
+        out7[3 * n + i] = 0.0;
+        out7[4 * n + i] = 0.0;
+        out7[5 * n + i] = 0.0;
+        out7[6 * n + i] = m ? static_cast<double>(m[i]) : 0.0;
+    }
+}
+
+// Offset of the block of sources whose coordinates equal the targets' bit for bit, or -1.
+int64_t find_target_block(const float *sx, const float *sy, const float *sz, int64_t n_src, const float *tx,
+                          const float *ty, const float *tz, int64_t n_tgt)
+{
+    if (n_tgt < 1 || n_tgt > n_src) return -1;
+    const size_t tb = static_cast<size_t>(n_tgt) * sizeof(float);
+    uint32_t first;
+    memcpy(&first, tx, sizeof first);
+    const uint32_t *bits = reinterpret_cast<const uint32_t *>(sx);
+    int tries = 0;
+    for (int64_t off = 0; off + n_tgt <= n_src; ++off) {
+        if (bits[off] != first) continue;
+        if (memcmp(sx + off, tx, tb) == 0 && memcmp(sy + off, ty, tb) == 0 && memcmp(sz + off, tz, tb) == 0) return off;
+        if (++tries >= 64) break;       // many sources share the first target's x (a lattice): give up
+    }
+    return -1;
+}
+}  // namespace
+
+static bool potential_plan_worthwhile(int64_t n_src, int64_t n_tgt)
+{
+    const char *e = getenv("HALMA_POT_PLAN_MIN_PAIRS");          // unset or <= 0: never
+    const double min_pairs = e ? atof(e) : 0.0;
+    if (min_pairs <= 0.0 || n_src < 1 || n_tgt < 1) return false;
+    return static_cast<double>(n_src) * static_cast<double>(n_tgt) >= min_pairs;
+}
+
+static int potential_via_plan(int device, const float *sm, const float *sx, const float *sy, const float *sz,
+                              int64_t n_src, const float *tx, const float *ty, const float *tz, int64_t n_tgt,
+                              float *out_be)
+{
+    const size_t tb = static_cast<size_t>(n_tgt) * sizeof(float);
+    const int64_t off = find_target_block(sx, sy, sz, n_src, tx, ty, tz, n_tgt);
+    const bool block = off >= 0;
+    // external groups: the sources before and after the block, or all of them
+    int64_t g_begin[2], g_count[2];
+    int n_groups = 0, n_pre = 0;
+    if (block) {
+        if (off > 0) {
+            g_begin[n_groups] = 0;
+            g_count[n_groups++] = off;
+            n_pre = 1;
+        }
+        if (off + n_tgt < n_src) {
+            g_begin[n_groups] = off + n_tgt;
+            g_count[n_groups++] = n_src - off - n_tgt;
+        }
+    } else {
+        g_begin[0] = 0;
+        g_count[0] = n_src;
+        n_groups = 1;
+    }
+    halma_unbind_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = static_cast<int32_t>(sizeof cfg);
+    cfg.device = device;
+    cfg.mode = HALMA_MODE_FAST;
+    cfg.n_groups = n_groups;
+    cfg.n_pre = n_pre;
+    cfg.vb_fixed = 1;
+    cfg.max_iter = 1;
+    cfg.G = 1.0;
+    cfg.kappa = 1.0;
+    cfg.n_ranks = 1;
+    cfg.symmetric = block ? 1 : 0;
+    const int64_t offsets[2] = {0, n_tgt};
+    const int64_t eo[2][2] = {{0, n_groups > 0 ? g_count[0] : 0}, {0, n_groups > 1 ? g_count[1] : 0}};
+    const int64_t *eop[2] = {eo[0], eo[1]};
+    halma_plan *P = nullptr;
+    int rc = halma_plan_create(&cfg, 1, offsets, n_groups ? eop : nullptr, &P);
+    if (rc == HALMA_ERR_TOO_LARGE) return kPlanPathDeclined;      // the direct path takes up to 2^31-16 of each
+    if (rc) return rc;
+    struct Guard {
+        halma_plan *p;
+        ~Guard() { halma_plan_destroy(p); }
+    } guard{P};
+    if (!P->np) return kPlanPathDeclined;          // e.g. too many particles for the sorted copies
+    cudaStream_t s = P->stream;
+    g_alloc_stream = s;
+    {
+        // targets -> the plan's float64 member arrays (exact), velocities zero, masses of the block or zero
+        DBuf<float> stage;
+        CU_TRY(stage.alloc(4 * static_cast<size_t>(n_tgt)));
+        const float *h[4] = {tx, ty, tz, block ? sm + off : nullptr};
+        for (int k = 0; k < 4; ++k)
+            if (h[k]) CU_TRY(cudaMemcpyAsync(stage.p + k * n_tgt, h[k], tb, cudaMemcpyHostToDevice, s));
+        const int grid = static_cast<int>(std::min<int64_t>((n_tgt + 255) / 256, P->ctx->sm_count * 8));
+        k_widen_members<<<grid, 256, 0, s>>>(stage.p, stage.p + n_tgt, stage.p + 2 * n_tgt,
+                                             block ? stage.p + 3 * n_tgt : nullptr, n_tgt, P->d_in.p);
+        CU_TRY(cudaGetLastError());
+        P->members_up = true;
+        P->sorted_dirty = true;
+    }
+    // the external groups are float32 already: straight into their packed segments (one halo: group g starts
+    // where group g-1 ended, rounded up to 4 elements, plan_build)
+    const size_t NE = static_cast<size_t>(P->n_ext_pad);
+    int64_t seg_begin = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const size_t sb = static_cast<size_t>(g_count[g]) * sizeof(float);
+        float *e = P->d_ext.p + seg_begin;
+        CU_TRY(cudaMemcpyAsync(e, sx + g_begin[g], sb, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(e + NE, sy + g_begin[g], sb, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(e + 2 * NE, sz + g_begin[g], sb, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(e + 3 * NE, sm + g_begin[g], sb, cudaMemcpyHostToDevice, s));
+        P->group_up[g] = true;
+        seg_begin += up4(g_count[g]);
+    }
+    if (!block) P->pp.ext_only = 1;
+    const double vb0[3] = {0.0, 0.0, 0.0};
+    rc = halma_plan_set_vb(P, vb0);
+    if (!rc) rc = halma_plan_run(P, nullptr);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(out_be, P->d_be.p, tb, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return HALMA_OK;
 }

@@ -196,3 +196,48 @@ def test_exact_outside_the_safe_window_falls_back_bit_exactly():
     ref = ora(ms, xs, ys, zs, tx, ty, tz, "f32seq")
     assert np.array_equal(bits(out), bits(ref))
     assert np.isinf(out[-1]) or out[-1] > 1e20          # the subnormal separations really were exercised
+
+
+def test_large_calls_through_a_plan(monkeypatch):
+    """HALMA_POT_PLAN_MIN_PAIRS=<pairs> (opt-in): large FAST calls of halma_potential_f32 run as a one-pass plan --
+    predicate-free kernel + correction tickets, symmetric self-term where the targets are a block of the sources.
+    Every shape the reference's callers have, against the direct (predicated) path and the float64 oracle."""
+    rng = np.random.default_rng(77)
+    st = synth.plummer_stars(50_000, 6 * synth.KPC, 1e6, rng)
+    synth.add_coincident_pairs(st, 5, rng)                      # shared coordinates -> correction tickets
+    gas = synth.lattice_gas(30_000, synth.CELL, rng, m_total=5e9)
+    dm = synth.dm_cloud(4_000, 20 * synth.KPC, 1e7, rng)
+    cat = lambda k, *ps: np.concatenate([getattr(p, k) for p in ps])       # noqa: E731
+    all_src = [cat(k, gas, st, dm) for k in ("mass", "x", "y", "z")]
+    cases = {
+        # targets ARE the sources (gas-gas of RPS on the lattice; stars-stars of most_bound_particle)
+        "self lattice": ([gas.mass, gas.x, gas.y, gas.z], gas),
+        "self stars": ([st.mass, st.x, st.y, st.z], st),
+        # targets are a block of the sources (escape_velocity_unbinding_fortran: concat(gas, stars, DM) -> stars)
+        "block": (all_src, st),
+        # block at the very start / end of the sources
+        "block first": (all_src, gas),
+        "block last": (all_src, dm),
+        # targets are other particles (stars -> gas)
+        "cross": ([st.mass, st.x, st.y, st.z], gas),
+        # ... some of which coincide with sources (a sampled subset of the gas as sources, halo_gas.py:307-321):
+        # zero separations outside any own tile -> the plan falls back to the predicated kernel
+        "cross coincident": ([a[len(gas) // 6:5 * len(gas) // 6] for a in (gas.mass, gas.x, gas.y, gas.z)], gas),
+    }
+    monkeypatch.setenv("HALMA_NP_MIN_PAIRS", "0")               # plans of any size on the predicate-free kernel
+    for name, (src, tgt) in cases.items():
+        monkeypatch.setenv("HALMA_POT_PLAN_MIN_PAIRS", "0")
+        direct = gpu(*src, tgt.x, tgt.y, tgt.z, "fast")
+        monkeypatch.setenv("HALMA_POT_PLAN_MIN_PAIRS", "1")
+        plan = gpu(*src, tgt.x, tgt.y, tgt.z, "fast")
+        assert plan.dtype == np.float32 and plan.shape == direct.shape, name
+        np.testing.assert_allclose(plan, direct, rtol=FAST_RTOL, err_msg=name)
+        pick = rng.choice(len(tgt), 300, replace=False)
+        ref = ora(*src, tgt.x[pick], tgt.y[pick], tgt.z[pick], "f64acc")
+        assert np.max(np.abs(plan[pick].astype(np.float64) / ref - 1)) < FAST_RTOL, name
+        again = gpu(*src, tgt.x, tgt.y, tgt.z, "fast")
+        assert np.array_equal(bits(again), bits(plan)), name           # bit-reproducible
+        # EXACT mode never takes the plan path
+        if name == "block last":
+            assert np.array_equal(bits(gpu(*src, tgt.x, tgt.y, tgt.z, "exact")), bits(ora(*src, tgt.x, tgt.y, tgt.z, "f32seq")))
+    monkeypatch.delenv("HALMA_POT_PLAN_MIN_PAIRS")
