@@ -1407,20 +1407,21 @@ extern "C" int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n, cons
 }
 
 // ---------------------------------------------------------------------------------------
-// brute_force_binding_energy through a one-pass plan (large FAST calls of halma_potential_f32; opt-in with
-// HALMA_POT_PLAN_MIN_PAIRS=<pairs>, e.g. 1e10).
+// brute_force_binding_energy through a one-pass plan: large FAST calls of halma_potential_f32 whose targets
+// are also sources (from HALMA_POT_PLAN_MIN_PAIRS pairs on, default 1e10; 0 = never).
 //
 // The direct path (potential_dev) runs the predicated kernel.  For a large call it pays to build the sorted
-// source copies once and use the predicate-free kernel + correction tickets of the plans, and where targets
-// are also sources the symmetric self-term on top.  The reference's callers come in three shapes:
+// source copies once and use the predicate-free kernel + correction tickets of the plans, with the symmetric
+// self-term on top.  The reference's callers come in three shapes:
 //   * the targets ARE the sources (gas-gas of RPS, halo_gas.py:306-328; stars-stars of most_bound_particle,
-//     :602-622);
+//     :602-622): 84.8 -> 47.1 ms for 5e5 gas cells, host arrays in and out (profiles/bench_f2py_call_r01.jsonl);
 //   * the targets are a block of the sources (escape_velocity_unbinding_fortran, halo_properties.py:333-339:
-//     sources = concat(gas, stars, DM), targets = the stars);
-//   * the targets are other particles (DM -> gas, stars -> gas).
-// In the first two the block becomes the plan's members and the sources before / after it external groups; in
-// the third the targets are massless members that are left out of the source list (PotParams::ext_only) and the
-// sources one external group.  One pass, fixed zero bulk velocity: out_be is the plan's `be`.
+//     sources = concat(gas, stars, DM), targets = the stars): 49.9 -> 37.1 ms for 2e5 stars in 7e5 sources;
+//   * the targets are other particles (DM -> gas, stars -> gas): these stay on the direct path -- as massless
+//     members left out of the source list they gained 9 %, and targets that coincide with sources (a sampled
+//     subset of the gas as sources, halo_gas.py:307-321) would send every such call through the fallback.
+// The block becomes the plan's members, the sources before / after it external groups.  One pass, fixed zero
+// bulk velocity: out_be is the plan's `be`.
 // ---------------------------------------------------------------------------------------
 namespace {
 __global__ void k_widen_members(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
@@ -1459,8 +1460,8 @@ int64_t find_target_block(const float *sx, const float *sy, const float *sz, int
 
 static bool potential_plan_worthwhile(int64_t n_src, int64_t n_tgt)
 {
-    const char *e = getenv("HALMA_POT_PLAN_MIN_PAIRS");          // unset or <= 0: never
-    const double min_pairs = e ? atof(e) : 0.0;
+    const char *e = getenv("HALMA_POT_PLAN_MIN_PAIRS");          // <= 0: never
+    const double min_pairs = e ? atof(e) : 1e10;
     if (min_pairs <= 0.0 || n_src < 1 || n_tgt < 1) return false;
     return static_cast<double>(n_src) * static_cast<double>(n_tgt) >= min_pairs;
 }
@@ -1471,24 +1472,18 @@ static int potential_via_plan(int device, const float *sm, const float *sx, cons
 {
     const size_t tb = static_cast<size_t>(n_tgt) * sizeof(float);
     const int64_t off = find_target_block(sx, sy, sz, n_src, tx, ty, tz, n_tgt);
-    const bool block = off >= 0;
-    // external groups: the sources before and after the block, or all of them
+    if (off < 0) return kPlanPathDeclined;
+    // external groups: the sources before and after the block
     int64_t g_begin[2], g_count[2];
     int n_groups = 0, n_pre = 0;
-    if (block) {
-        if (off > 0) {
-            g_begin[n_groups] = 0;
-            g_count[n_groups++] = off;
-            n_pre = 1;
-        }
-        if (off + n_tgt < n_src) {
-            g_begin[n_groups] = off + n_tgt;
-            g_count[n_groups++] = n_src - off - n_tgt;
-        }
-    } else {
-        g_begin[0] = 0;
-        g_count[0] = n_src;
-        n_groups = 1;
+    if (off > 0) {
+        g_begin[n_groups] = 0;
+        g_count[n_groups++] = off;
+        n_pre = 1;
+    }
+    if (off + n_tgt < n_src) {
+        g_begin[n_groups] = off + n_tgt;
+        g_count[n_groups++] = n_src - off - n_tgt;
     }
     halma_unbind_config cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -1502,7 +1497,7 @@ static int potential_via_plan(int device, const float *sm, const float *sx, cons
     cfg.G = 1.0;
     cfg.kappa = 1.0;
     cfg.n_ranks = 1;
-    cfg.symmetric = block ? 1 : 0;
+    cfg.symmetric = 1;
     const int64_t offsets[2] = {0, n_tgt};
     const int64_t eo[2][2] = {{0, n_groups > 0 ? g_count[0] : 0}, {0, n_groups > 1 ? g_count[1] : 0}};
     const int64_t *eop[2] = {eo[0], eo[1]};
@@ -1518,15 +1513,15 @@ static int potential_via_plan(int device, const float *sm, const float *sx, cons
     cudaStream_t s = P->stream;
     g_alloc_stream = s;
     {
-        // targets -> the plan's float64 member arrays (exact), velocities zero, masses of the block or zero
+        // targets -> the plan's float64 member arrays (exact), velocities zero, masses of the block
         DBuf<float> stage;
         CU_TRY(stage.alloc(4 * static_cast<size_t>(n_tgt)));
-        const float *h[4] = {tx, ty, tz, block ? sm + off : nullptr};
+        const float *h[4] = {tx, ty, tz, sm + off};
         for (int k = 0; k < 4; ++k)
             if (h[k]) CU_TRY(cudaMemcpyAsync(stage.p + k * n_tgt, h[k], tb, cudaMemcpyHostToDevice, s));
         const int grid = static_cast<int>(std::min<int64_t>((n_tgt + 255) / 256, P->ctx->sm_count * 8));
         k_widen_members<<<grid, 256, 0, s>>>(stage.p, stage.p + n_tgt, stage.p + 2 * n_tgt,
-                                             block ? stage.p + 3 * n_tgt : nullptr, n_tgt, P->d_in.p);
+                                             stage.p + 3 * n_tgt, n_tgt, P->d_in.p);
         CU_TRY(cudaGetLastError());
         P->members_up = true;
         P->sorted_dirty = true;
@@ -1545,7 +1540,6 @@ static int potential_via_plan(int device, const float *sm, const float *sx, cons
         P->group_up[g] = true;
         seg_begin += up4(g_count[g]);
     }
-    if (!block) P->pp.ext_only = 1;
     const double vb0[3] = {0.0, 0.0, 0.0};
     rc = halma_plan_set_vb(P, vb0);
     if (!rc) rc = halma_plan_run(P, nullptr);

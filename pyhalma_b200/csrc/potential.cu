@@ -688,9 +688,7 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
         // pass (externals and corrections included) and no correction ticket is needed.
         const bool incr = REUSE && p.incr_enabled && p.incr[tk.h];
         int filt = 0, nphase = 1;
-        if (REUSE && p.ext_only) {
-            filt = 2;      // the f2py-level call through a plan: the targets are not sources
-        } else if (REUSE && p.cache_ext && hd->n_ext > 0 && !incr) {
+        if (REUSE && p.cache_ext && hd->n_ext > 0 && !incr) {
             if (st->pass == 0) {
                 filt = 1;
                 nphase = 2;
@@ -1065,12 +1063,12 @@ cudaError_t potential_launch(const PotParams &p, int mode, int variant, int grid
         k_potential_exact<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else if (p.np_enabled && !p.redo_only && p.sym_enabled) {
         const int per_sm = variant < 16 && g_bps[variant] > 0 ? g_bps[variant] : 1;
-        if (p.cache_ext || p.incr_enabled || p.ext_only)
+        if (p.cache_ext || p.incr_enabled)
             kSymReuseKernel<<<grid_blocks / per_sm * (g_sym_reuse_bps > 0 ? g_sym_reuse_bps : 1), kPotentialBlock,
                               kSmemBytes, stream>>>(p);
         else
             kSymKernel<<<grid_blocks / per_sm * (g_sym_bps > 0 ? g_sym_bps : 1), kPotentialBlock, kSmemBytes, stream>>>(p);
-    } else if (p.np_enabled && !p.redo_only && (p.cache_ext || p.incr_enabled || p.ext_only))
+    } else if (p.np_enabled && !p.redo_only && (p.cache_ext || p.incr_enabled))
         kVariants[variant].np_reuse<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else if (p.np_enabled && !p.redo_only)
         kVariants[variant].np<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);

@@ -114,9 +114,15 @@ def test_cfg2_full_size_fast_sampled_check_and_linearity():
     pick = np.random.default_rng(1).choice(len(s), 256, replace=False)
     ref = ora(*src, s.x[pick], s.y[pick], s.z[pick], "f64acc")
     assert np.max(np.abs(got[pick].astype(np.float64) / ref - 1)) < FAST_RTOL
-    # linearity: scaling every mass by 4 scales Phi by exactly 4 (power of two)
-    got4 = gpu(src[0] * 4, src[1], src[2], src[3], s.x[:50_000], s.y[:50_000], s.z[:50_000], "fast")
-    assert np.array_equal(bits(got4), bits(got[:50_000] * f32(4)))
+    # linearity: scaling every mass by 4 scales Phi by exactly 4 (power of two); the same call shape, because
+    # a call this large runs as a plan (the stars are a block of the sources) whose tiling depends on the shape
+    got4 = gpu(src[0] * 4, src[1], src[2], src[3], s.x, s.y, s.z, "fast")
+    assert np.array_equal(bits(got4), bits(got * f32(4)))
+    # ... and on the direct path (a call below the plan threshold)
+    few = gpu(src[0], src[1], src[2], src[3], s.x[:10_000], s.y[:10_000], s.z[:10_000], "fast")
+    few4 = gpu(src[0] * 4, src[1], src[2], src[3], s.x[:10_000], s.y[:10_000], s.z[:10_000], "fast")
+    assert np.array_equal(bits(few4), bits(few * f32(4)))
+    np.testing.assert_allclose(few, got[:10_000], rtol=FAST_RTOL)
     # additivity over a source partition, in float64 tolerance
     a = gpu(g.mass, g.x, g.y, g.z, s.x[:20_000], s.y[:20_000], s.z[:20_000], "fast").astype(np.float64)
     b = gpu(s.mass, s.x, s.y, s.z, s.x[:20_000], s.y[:20_000], s.z[:20_000], "fast").astype(np.float64)
@@ -199,9 +205,10 @@ def test_exact_outside_the_safe_window_falls_back_bit_exactly():
 
 
 def test_large_calls_through_a_plan(monkeypatch):
-    """HALMA_POT_PLAN_MIN_PAIRS=<pairs> (opt-in): large FAST calls of halma_potential_f32 run as a one-pass plan --
-    predicate-free kernel + correction tickets, symmetric self-term where the targets are a block of the sources.
-    Every shape the reference's callers have, against the direct (predicated) path and the float64 oracle."""
+    """Large FAST calls of halma_potential_f32 whose targets are a block of the sources run as a one-pass plan
+    (from HALMA_POT_PLAN_MIN_PAIRS pairs on, default 1e10): predicate-free kernel + correction tickets + symmetric
+    self-term.  Every shape the reference's callers have, against the direct (predicated) path and the float64
+    oracle; calls whose targets are other particles stay on the direct path."""
     rng = np.random.default_rng(77)
     st = synth.plummer_stars(50_000, 6 * synth.KPC, 1e6, rng)
     synth.add_coincident_pairs(st, 5, rng)                      # shared coordinates -> correction tickets
@@ -218,10 +225,9 @@ def test_large_calls_through_a_plan(monkeypatch):
         # block at the very start / end of the sources
         "block first": (all_src, gas),
         "block last": (all_src, dm),
-        # targets are other particles (stars -> gas)
+        # targets are other particles (stars -> gas): direct path
         "cross": ([st.mass, st.x, st.y, st.z], gas),
-        # ... some of which coincide with sources (a sampled subset of the gas as sources, halo_gas.py:307-321):
-        # zero separations outside any own tile -> the plan falls back to the predicated kernel
+        # ... some of which coincide with sources (a sampled subset of the gas as sources, halo_gas.py:307-321)
         "cross coincident": ([a[len(gas) // 6:5 * len(gas) // 6] for a in (gas.mass, gas.x, gas.y, gas.z)], gas),
     }
     monkeypatch.setenv("HALMA_NP_MIN_PAIRS", "0")               # plans of any size on the predicate-free kernel
@@ -237,6 +243,8 @@ def test_large_calls_through_a_plan(monkeypatch):
         assert np.max(np.abs(plan[pick].astype(np.float64) / ref - 1)) < FAST_RTOL, name
         again = gpu(*src, tgt.x, tgt.y, tgt.z, "fast")
         assert np.array_equal(bits(again), bits(plan)), name           # bit-reproducible
+        if name.startswith("cross"):
+            assert np.array_equal(bits(plan), bits(direct)), name      # not a block of the sources: same path
         # EXACT mode never takes the plan path
         if name == "block last":
             assert np.array_equal(bits(gpu(*src, tgt.x, tgt.y, tgt.z, "exact")), bits(ora(*src, tgt.x, tgt.y, tgt.z, "f32seq")))
