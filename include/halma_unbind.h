@@ -81,6 +81,11 @@ int halma_potential_f32(int device, int mode,
                         const float *tgt_x, const float *tgt_y, const float *tgt_z,
                         int64_t n_tgt, float *out_be);
 
+/* Host-only helper of the above (no GPU needed): the offset of the block of sources whose coordinates
+ * equal the targets' bit for bit, in the same order, or -1.  0 with n_tgt == n_src is a self call. */
+int64_t halma_find_target_block(const float *src_x, const float *src_y, const float *src_z, int64_t n_src,
+                                const float *tgt_x, const float *tgt_y, const float *tgt_z, int64_t n_tgt);
+
 /* Same with DEVICE pointers (16-byte aligned) on `stream` (a cudaStream_t, 0 = default);
  * asynchronous.  workspace: device scratch of halma_potential_workspace_bytes(). */
 int64_t halma_potential_workspace_bytes(int64_t n_src, int64_t n_tgt);

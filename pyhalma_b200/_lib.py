@@ -27,6 +27,7 @@ EXPORTS = (
     "halma_snapshot_create", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_snapshot_upload_patch",
     "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_fetch", "halma_last_kernel_ms",
     "halma_snapshot_result_device", "halma_snapshot_fetch_star", "halma_selftest_exact_arith",
+    "halma_find_target_block",
 )
 
 
@@ -116,10 +117,13 @@ def lib() -> C.CDLL:
     L.halma_snapshot_result_device.argtypes = [vp] * 4
     L.halma_snapshot_fetch_star.argtypes = [vp, i64, vp, vp]
     L.halma_selftest_exact_arith.argtypes = [i32, i64, C.c_uint64, C.POINTER(i64)]
+    L.halma_find_target_block.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64]
+    L.halma_find_target_block.restype = i64
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("halma_last_error", "halma_potential_workspace_bytes", "halma_plan_destroy",
-                        "halma_comm_destroy", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_last_kernel_ms"):
+                        "halma_comm_destroy", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_last_kernel_ms",
+                        "halma_find_target_block"):
             fn.restype = i32
     if L.halma_abi_version() != 1:
         raise ImportError("libhalma_unbind ABI version mismatch")

@@ -1458,6 +1458,14 @@ int64_t find_target_block(const float *sx, const float *sy, const float *sz, int
 }
 }  // namespace
 
+extern "C" int64_t halma_find_target_block(const float *src_x, const float *src_y, const float *src_z, int64_t n_src,
+                                           const float *tgt_x, const float *tgt_y, const float *tgt_z, int64_t n_tgt)
+{
+    if (n_src < 0 || n_tgt < 0) return -1;
+    if (n_tgt > 0 && (!src_x || !src_y || !src_z || !tgt_x || !tgt_y || !tgt_z)) return -1;
+    return find_target_block(src_x, src_y, src_z, n_src, tgt_x, tgt_y, tgt_z, n_tgt);
+}
+
 static bool potential_plan_worthwhile(int64_t n_src, int64_t n_tgt)
 {
     const char *e = getenv("HALMA_POT_PLAN_MIN_PAIRS");          // <= 0: never

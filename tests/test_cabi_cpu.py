@@ -109,3 +109,36 @@ def test_halo_results_view_matches_struct_layout():
     assert list(r.field("n_bound")) == [0, 7, 0] and r.field("com").shape == (3, 3)
     with pytest.raises(IndexError):
         r[3]
+
+
+def test_find_target_block_host_helper():
+    """halma_potential_f32 runs a large call as a plan when the targets are a block of the sources
+    (csrc/api.cu::potential_via_plan); the search for that block is plain host code."""
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    f32 = np.float32
+
+    def find(src, tgt):
+        s = [np.ascontiguousarray(a, f32) for a in src]
+        t = [np.ascontiguousarray(a, f32) for a in tgt]
+        return L.halma_find_target_block(*[a.ctypes.data for a in s], len(s[0]), *[a.ctypes.data for a in t], len(t[0]))
+
+    x, y, z = rng.normal(size=(3, 1000))
+    assert find((x, y, z), (x, y, z)) == 0                                        # self call (separate copies)
+    assert find((x, y, z), (x[300:700], y[300:700], z[300:700])) == 300           # block in the middle
+    assert find((x, y, z), (x[:10], y[:10], z[:10])) == 0 and find((x, y, z), (x[990:], y[990:], z[990:])) == 990
+    assert find((x[:500], y[:500], z[:500]), (x, y, z)) == -1                     # more targets than sources
+    y2 = y.copy()
+    y2[650] += 1.0
+    assert find((x, y, z), (x[300:700], y2[300:700], z[300:700])) == -1           # one coordinate differs
+    assert find((x, y, z), (x[300:700][::-1], y[300:700][::-1], z[300:700][::-1])) == -1      # other order
+    assert find((x, y, z), (x[:0], y[:0], z[:0])) == -1 and find((x[:0], y[:0], z[:0]), (x[:0], y[:0], z[:0])) == -1
+    # a lattice: many sources share the first target's x; the block itself is still the first candidate
+    gx, gy, gz = [a.ravel() for a in np.meshgrid(np.arange(8.0), np.arange(8.0), np.arange(8.0), indexing="ij")]
+    assert find((gx, gy, gz), (gx, gy, gz)) == 0
+    assert find((np.r_[x, gx], np.r_[y, gy], np.r_[z, gz]), (gx, gy, gz)) == 1000
+    # ... and when it is not among the first 64 sources with that x the search gives up (direct path)
+    assert find((np.r_[gx, gx[:100], gx], np.r_[gy, gy[:100] + 0.5, gy], np.r_[gz, gz[:100], gz]),
+                (gx[:100], gy[:100] + 0.5, gz[:100])) in (-1, 512)
+    # -0.0 and +0.0 are different bit patterns: not a block (the call then takes the direct path, same result)
+    assert find(([0.0, 1.0], [0.0, 1.0], [0.0, 1.0]), ([-0.0, 1.0], [0.0, 1.0], [0.0, 1.0])) == -1
