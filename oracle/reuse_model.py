@@ -29,6 +29,8 @@ import numpy as np
 from . import oracle as O
 
 CHUNK = 32      # sources per float32 partial sum (csrc/potential.cu: kFlushQuads * 4)
+INCR_HEAVY = 0.8    # csrc/potential.cu::kIncrHeavy: an incremental pass in which the removed members carried more
+                    # than this share of some member's kept potential is redone as a full predicated pass
 
 
 def _terms(tx, ty, tz, sm, sx, sy, sz):
@@ -79,8 +81,10 @@ class ModelResult:
 
 
 def unbind_halo(x, y, z, vx, vy, vz, mass, *, ext: Sequence = (), kappa: float = 9.0, vb_fixed=None,
-                max_iter: int = 64, cache_external: bool = True, incremental: bool = True) -> ModelResult:
-    """ext: sequence of (mass, x, y, z) fixed source groups (their order does not matter in FAST mode)."""
+                max_iter: int = 64, cache_external: bool = True, incremental: bool = True,
+                heavy_guard: bool = True) -> ModelResult:
+    """ext: sequence of (mass, x, y, z) fixed source groups (their order does not matter in FAST mode).
+    heavy_guard=False switches the INCR_HEAVY safeguard off (to show what it is for)."""
     f32 = np.float32
     X, Y, Z, M = (np.asarray(a, np.float64).astype(f32) for a in (x, y, z, mass))
     vx, vy, vz, m64 = (np.asarray(a, np.float64) for a in (vx, vy, vz, mass))
@@ -103,12 +107,23 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, ext: Sequence = (), kappa: float =
     while len(idx) > 0 and it < max_iter:
         t = (X[idx], Y[idx], Z[idx])
         n = len(idx)
+        fallback = False
         if incr_next:
             r = removed
-            phi = phi_keep[idx] - _free_sum(*t, M[r], X[r], Y[r], Z[r], predicate=True)
-            evals += n * len(r)
-            kinds.append("incr")
-        else:
+            gone = _free_sum(*t, M[r], X[r], Y[r], Z[r], predicate=True)
+            fallback = heavy_guard and bool(np.any(np.abs(gone) > INCR_HEAVY * np.abs(phi_keep[idx])))
+            phi = phi_keep[idx] - gone
+            if not fallback:
+                evals += n * len(r)
+                kinds.append("incr")
+        if fallback:
+            # the whole halo again, with the reference's predicate (the predicated kernel): complete in itself
+            src = (np.concatenate((M[idx], em)), np.concatenate((X[idx], ex)), np.concatenate((Y[idx], ey)),
+                   np.concatenate((Z[idx], ez)))
+            phi = _free_sum(*t, *src, predicate=True)
+            evals += n * (n + n_ext)
+            kinds.append("fallback")
+        elif not incr_next:
             phi = _free_sum(*t, M[idx], X[idx], Y[idx], Z[idx])
             evals += n * n
             cached = cache_external and it > 0
@@ -140,7 +155,7 @@ def unbind_halo(x, y, z, vx, vy, vz, mass, *, ext: Sequence = (), kappa: float =
         new_idx = idx[bound]
         removed = idx[~bound]
         changed = len(new_idx) != len(idx)
-        incr_next = incremental and len(removed) > 0 and 2 * len(removed) <= len(new_idx)
+        incr_next = incremental and not fallback and len(removed) > 0 and 2 * len(removed) <= len(new_idx)
         idx = new_idx
         if not changed:
             break

@@ -901,6 +901,9 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     Q.incr = L.incr;
     Q.rem_cnt = L.rem_cnt;
     Q.incr_enabled = L.incr_enabled;
+    Q.widx[0] = L.widx[0];
+    Q.widx[1] = L.widx[1];
+    Q.phi_keep = L.phi_keep;
     Q.src[6] = F32Set{L.rx, L.ry, L.rz, L.rm};
     for (int a = 0; a < 3 && P->np; ++a) {
         Q.ax[a] = L.ax[a];

@@ -57,6 +57,8 @@ constexpr int kStageFloats = 4 * kTileJ;    // x | y | z | m
 constexpr int kFlushQuads = 8;              // flush float32 partials every 8 quads = 32 sources ...
 constexpr int kFlushQuadsNp = 16;           // ... or 64 in the predicate-free body, whose packed accumulator
                                             // keeps even and odd sources apart (32 terms per float32 sum)
+constexpr double kIncrHeavy = 0.8;          // incremental pass: largest removed share of a member's kept potential
+                                            // (error amplification 1 / (1 - 0.8) = 5 on ~1e-7)
 constexpr int kWarpsPerBlock = kPotentialBlock / 32;
 // ring stages + their mbarriers + the column partial sums of the symmetric tickets
 constexpr int kSmemBytes = kWarpsPerBlock * (kStages * (kStageFloats * 4 + 8) + kTileJ * 4);
@@ -722,6 +724,22 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const 
 #pragma unroll
                 for (int t = 0; t < T; ++t)
                     bad |= (tk.group * kGroup + t * 32 + lane < tk.n_tgt) && !(fabs(acc64[t]) <= 1.7976931348623157e308);
+                if (REUSE && incr) {
+                    // k_energy_flag will subtract this sum from the potential it kept; the difference carries the
+                    // rounding of the float32 partial sums in here, ~1e-7 of the sum.  That is far inside the
+                    // tolerance unless the removed members made up most of a member's potential (a tight pair
+                    // that lost its partner): removed > kIncrHeavy of the kept potential, tested per j-split piece
+                    // (conservatively: a total beyond the limit has a piece beyond limit / S).  Such a halo is
+                    // recomputed from scratch by the predicated kernel in this same pass.
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        const int i = tk.group * kGroup + t * 32 + lane;
+                        if (i < tk.n_tgt) {
+                            const int64_t os = hd->poff + (p.widx[parity][tbase + i] - hd->uoff);
+                            bad |= fabs(acc64[t]) * tk.S > kIncrHeavy * fabs(p.phi_keep[os]);
+                        }
+                    }
+                }
                 if (__any_sync(0xffffffffu, bad) && lane == 0) {
                     atomicExch(&p.halo_redo[tk.h], 1);
                     atomicExch(&p.st->redo_any, 1);

@@ -182,6 +182,42 @@ def test_duplicates_fall_back_and_recover(monkeypatch):
             assert np.all(O.energy_margin(o.energy, o.be32, 9.0)[diff] < BAND)
 
 
+def test_incremental_pass_that_removes_most_of_a_members_potential(monkeypatch):
+    # A tight pair: B sits 1e-7 Mpc from A and provides ~90 % of A's potential; B is an interloper and leaves in
+    # the first pass, A stays.  Subtracting B's term from A's kept potential would amplify the float32 rounding
+    # of that term ten times, so the incremental ticket hands the halo to the predicated kernel in that pass
+    # (csrc/potential.cu, kIncrHeavy): results as exact as the plain loop's, one pass counted as a full one.
+    monkeypatch.setenv("HALMA_NP_MIN_PAIRS", "0")
+    rng = np.random.default_rng(51)
+    p = synth.plummer_stars(3000, 2e-3, 1e6, rng, centre=(0.0, 0.0, 0.0), bulk_v=(0., 0., 0.), interloper_frac=0.1)
+    o0 = O.unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, kappa=9.0, variant="f64acc")
+    a = int(np.flatnonzero(o0.mask)[100])                       # a member that stays bound
+    b = int(np.flatnonzero(~o0.mask & (o0.be32 > 0))[0])        # one that leaves
+    x, y, z = p.x.copy(), p.y.copy(), p.z.copy()
+    vx, vy, vz = p.vx.copy(), p.vy.copy(), p.vz.copy()
+    x[b], y[b], z[b] = x[a] + 3e-8, y[a] + 4e-8, z[a] - 5e-8
+    vx[b], vy[b], vz[b] = 3e4, -2e4, 1e4                        # far beyond any escape velocity
+    args = (x, y, z, vx, vy, vz, p.mass)
+    o = O.unbind_halo(*args, kappa=9.0, variant="f64acc")
+    assert o.mask[a] and not o.mask[b] and o.n_iter >= 3
+    first = O.unbind_halo(*args, kappa=9.0, variant="f64acc", max_iter=1)
+    assert first.be32[a] > 5 * o.be32[a]                        # B carried most of A's potential
+    ref = unbind_halo(*args, kappa=9.0, mode="fast", cache_external=False, incremental=False)
+    r = unbind_halo(*args, kappa=9.0, mode="fast", cache_external=False, incremental=True)
+    assert np.array_equal(r.mask, ref.mask) and r.n_iter == ref.n_iter
+    np.testing.assert_allclose(r.be32, ref.be32, rtol=FAST_RTOL)
+    both = r.mask & o.mask
+    assert np.abs(r.be32[both].astype(np.float64) / o.be32[both] - 1).max() < FAST_RTOL
+    assert np.all(O.energy_margin(o.energy, o.be32, 9.0)[r.mask != o.mask] < BAND)
+    if np.array_equal(r.mask, o.mask):
+        # the second pass was NOT taken incrementally (it is counted as a full, predicated one) and the pass after
+        # a fallback is a full one: exactly the passes of the numpy model of the bookkeeping
+        m = RM.unbind_halo(*args, kappa=9.0, cache_external=False, incremental=True)
+        assert m.passes == ["full", "fallback", "full"]
+        assert r.stats.evaluations == m.evaluations
+        assert r.stats.evaluations > RM.expected_evaluations(o.n_bound_history, 0, cache_external=False, incremental=True)
+
+
 def test_reuse_forced_on_for_the_whole_battery():
     """The ragged / degenerate / duplicate / NaN / external-group / golden / full-size / graph battery of
     test_gpu_unbind.py with both options on and every plan forced onto the predicate-free kernel."""

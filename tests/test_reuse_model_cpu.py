@@ -64,3 +64,34 @@ def test_gas_lattice_model_with_fixed_bulk_velocity():
         assert m.n_iter == o.n_iter
     seen = o.be32 > 0
     assert np.abs(m.be32[seen].astype(np.float64) / o.be32[seen] - 1).max() < FAST_RTOL
+
+
+def tight_pair_case():
+    """A bound member A whose potential is ~94 % due to a neighbour B at 7e-8 Mpc that leaves in the first pass."""
+    rng = np.random.default_rng(51)
+    p = synth.plummer_stars(3000, 2e-3, 1e6, rng, centre=(0.0, 0.0, 0.0), bulk_v=(0., 0., 0.), interloper_frac=0.1)
+    o0 = O.unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, kappa=9.0, variant="f64acc")
+    a = int(np.flatnonzero(o0.mask)[100])
+    b = int(np.flatnonzero(~o0.mask & (o0.be32 > 0))[0])
+    x, y, z = p.x.copy(), p.y.copy(), p.z.copy()
+    vx, vy, vz = p.vx.copy(), p.vy.copy(), p.vz.copy()
+    x[b], y[b], z[b] = x[a] + 3e-8, y[a] + 4e-8, z[a] - 5e-8
+    vx[b], vy[b], vz[b] = 3e4, -2e4, 1e4
+    return (x, y, z, vx, vy, vz, p.mass), a, b
+
+
+def test_incremental_pass_needs_the_heavy_removal_guard():
+    """Subtracting a removed neighbour that carried most of a member's potential amplifies the float32 rounding
+    of that one term beyond the tolerance; the guard (csrc/potential.cu::kIncrHeavy, reuse_model.INCR_HEAVY)
+    redoes such a pass with the predicated kernel."""
+    args, a, b = tight_pair_case()
+    o = O.unbind_halo(*args, kappa=9.0, variant="f64acc")
+    assert o.mask[a] and not o.mask[b] and o.n_iter >= 3
+    seen = o.be32 > 0
+    err = lambda m: np.abs(m.be32[seen].astype(np.float64) / o.be32[seen] - 1).max()      # noqa: E731
+    unguarded = RM.unbind_halo(*args, kappa=9.0, cache_external=False, heavy_guard=False)
+    assert unguarded.passes[:2] == ["full", "incr"] and err(unguarded) > FAST_RTOL        # what the guard is for
+    guarded = RM.unbind_halo(*args, kappa=9.0, cache_external=False)
+    assert guarded.passes == ["full", "fallback", "full"]          # a pass that fell back is followed by a full one
+    assert err(guarded) < FAST_RTOL and np.array_equal(guarded.mask, o.mask) and guarded.n_iter == o.n_iter
+    assert guarded.evaluations > RM.expected_evaluations(o.n_bound_history, 0, cache_external=False, incremental=True)
