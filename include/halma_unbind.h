@@ -152,11 +152,13 @@ typedef struct halma_unbind_config {
                                 kept per member in float64 and added in every later pass.  Same terms, same
                                 tolerances; halma_run_stats.evaluations counts what was actually evaluated. */
     int32_t incremental;     /* 1 (FAST mode, predicate-free path; also in split mode): when a pass removed at
-                                most a third of a halo's members, the next pass of that halo only evaluates survivors x removed members and
-                                subtracts that from the predicate-free sum kept from the pass before (the
-                                same per-pair terms; the difference is float32 partial-sum rounding,
-                                ~1e-7 of the removed contribution).  A pass that fell back to the predicated
-                                kernel is always followed by a full pass.                                */
+                                most a third of a halo's members, the next pass of that halo only evaluates
+                                survivors x removed members (with the reference's predicate) and subtracts
+                                that from the complete float64 potential kept from the pass before: the same
+                                per-pair terms, the difference is float32 partial-sum rounding, ~1e-7 of the
+                                removed contribution.  If the removed members carried more than 80 % of some
+                                member's potential, or the pass fell back to the predicated kernel for any
+                                other reason, the halo is recomputed in full instead.                        */
 } halma_unbind_config;
 
 typedef struct halma_halo_result {
