@@ -1,5 +1,5 @@
 #!/bin/bash
-# Split mode with incremental passes on 2 GPUs: gpurun --gpus 2 --timeout 600 -- 'bash scripts/gpu_split2_reuse.sh'
+# Split mode with incremental passes on 2 GPUs: gpurun --gpus 2 --timeout 600 -- 'bash scripts/gpu_split2.sh'
 set -x
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests/test_gpu_split.py -q -x 2>&1 | tail -15 | tee gpurun_out/pytest_split.txt
