@@ -136,6 +136,93 @@ def test_split_protocol_world_size_2_gloo():
     assert all(results)
 
 
+def _split_incremental_worker(rank, world, port, q):
+    """Emulates the split-mode LOOP with incremental passes (csrc/api.cu::enqueue_pass, DESIGN.md §5.10) with the
+    CPU oracle: every rank keeps the whole halo and the kept potentials (kernels 2-3 run replicated), evaluates
+    only the target groups it owns -- against all current sources in a full pass, against the members the last
+    pass removed in an incremental one -- and ONE all-reduce per pass completes the sums.  No other exchange: the
+    full / incremental decision depends on replicated state only, so every rank must take the same one, and the
+    result must be the single-process unbinding."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = synth.config1(1500, 700, n_dm=100)
+        s, g, d = c.stars, c.gas, c.dm
+        ext = [np.concatenate((getattr(g, k), getattr(d, k))) for k in ("mass", "x", "y", "z")]
+        N = len(s)
+        idx = np.arange(N)
+        keep = np.zeros(N)
+        be_out = np.zeros(N, np.float32)
+        removed = np.zeros(0, np.int64)
+        incr, kinds, it = False, [], 0
+        while len(idx) and it < 64:
+            own = sharding.split_owner(len(idx), 128, world) == rank        # groups of the CURRENT member list
+            if incr:
+                src = [getattr(s, k)[removed] for k in ("mass", "x", "y", "z")]
+            else:
+                src = [np.concatenate((getattr(s, k)[idx], e)) for k, e in zip(("mass", "x", "y", "z"), ext)]
+            part = np.zeros(len(idx))
+            if own.any():
+                t = idx[own]
+                part[own] = O.brute_force_binding_energy_fortran(*src, s.x[t], s.y[t], s.z[t], variant="f64acc")
+            red = torch.from_numpy(part)
+            dist.all_reduce(red)                                            # the one collective of the pass
+            phi = keep[idx] - red.numpy() if incr else red.numpy()
+            keep[idx] = phi
+            kinds.append("incr" if incr else "full")
+            be = phi.astype(np.float32)
+            M = O.total_mass(idx, s.mass)
+            vb = O.CM_velocity(M, idx, s.vx, s.vy, s.vz, s.mass)
+            E = O.energy_step(be, s.vx[idx], s.vy[idx], s.vz[idx], vb[0], vb[1], vb[2], 9.0)
+            be_out[idx] = be
+            it += 1
+            bound = E <= 0.0
+            removed, new = idx[~bound], idx[bound]
+            incr = len(removed) > 0 and 2 * len(removed) <= len(new)
+            done = len(new) == len(idx)
+            idx = new
+            if done:
+                break
+        ref = O.unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, pre=[g.pos_mass()], post=[d.pos_mass()], kappa=9.0,
+                            variant="f64acc")
+        mask = np.zeros(N, bool)
+        mask[idx] = True
+        seen = ref.be32 > 0
+        ok = (np.array_equal(mask, ref.mask) and it == ref.n_iter and "incr" in kinds and kinds[0] == "full"
+              and float(np.abs(be_out[seen].astype(np.float64) / ref.be32[seen] - 1).max()) < 1e-6)
+        # every rank holds the same result, bit for bit
+        digest = hashlib.sha256(mask.tobytes() + be_out.tobytes() + repr(kinds).encode()).digest()
+        mine = torch.frombuffer(bytearray(digest), dtype=torch.uint8).clone()
+        others = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(others, mine)
+        q.put(bool(ok) and all(bool(torch.equal(o, mine)) for o in others))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_loop_with_incremental_passes_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_split_incremental_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(results)
+
+
 def test_cost_cuts_for_the_multi_stream_catalogue_path():
     from pyhalma_b200.unbind import cost_cuts
     sizes = np.array([10, 10, 1000, 10, 10, 10, 500, 500, 10, 10])
