@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HALMA_ABI_VERSION 1
+#define HALMA_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------ */
 #define HALMA_OK                0
@@ -53,6 +53,12 @@ extern "C" {
  *        reference terms to better than 1e-6 relative.                                   */
 #define HALMA_MODE_FAST   0
 #define HALMA_MODE_EXACT  1
+
+/* loop drivers (halma_unbind_config.use_graph) */
+#define HALMA_DRIVER_AUTO     0
+#define HALMA_DRIVER_GRAPH    1
+#define HALMA_DRIVER_ENQUEUE  2
+#define HALMA_DRIVER_FUSED    3
 
 const char *halma_last_error(void);
 int halma_abi_version(void);
@@ -134,11 +140,17 @@ typedef struct halma_unbind_config {
     double  kappa;           /* factor_v**2 (stars) or 2.0 (gas); cast to float32        */
     int32_t rank;            /* split mode: this process's rank ...                      */
     int32_t n_ranks;         /* ... of n_ranks sharing ONE halo by target groups (1 = off) */
-    int32_t use_graph;       /* 1: run the loop as ONE CUDA-graph launch (WHILE conditional node,
-                                condition set on the device by the scheduling kernel).  0: the host
-                                enqueues passes ahead of the device and learns about convergence from
-                                a pinned flag; gives per-launch CUDA-event timing in halma_run_stats.
-                                Ignored (0) in split mode.                                   */
+    int32_t use_graph;       /* loop driver (the field keeps its round-1 name; HALMA_DRIVER_*):
+                                0 AUTO: on one GPU the whole loop runs as ONE persistent cooperative kernel
+                                  (fused.cu: every pass inside the launch, grid barriers between the phases, no
+                                  host round trip; halma_run_stats.potential_ms comes from in-kernel timestamps);
+                                  split mode and the tuning kernel shapes use ENQUEUE.
+                                1 GRAPH: one CUDA-graph launch, a WHILE conditional node whose body is one pass
+                                  of stand-alone kernels; the scheduling kernel sets the condition on the device.
+                                2 ENQUEUE: the host enqueues passes of stand-alone kernels ahead of the device and
+                                  learns about convergence from a pinned flag; per-launch CUDA-event timing.
+                                3 FUSED: as AUTO, but an error where the persistent kernel cannot serve the plan.
+                                All drivers run the same phase code and give bit-identical results.       */
     int32_t symmetric;       /* 1 (FAST mode, plans large enough for the predicate-free kernel's throughput
                                 shape): every member x member pair of different 128-member tiles is
                                 evaluated once and feeds both particles' sums -- half the rsqrt work of the
@@ -180,16 +192,23 @@ typedef struct halma_halo_result {
 
 typedef struct halma_run_stats {
     double  total_ms;        /* CUDA-event time of the whole run on the plan's stream    */
-    double  potential_ms;    /* sum over potential-kernel launches (CUDA events); 0 with
-                                use_graph = 1, where single launches cannot be timed      */
-    int32_t potential_launches;
+    double  potential_ms;    /* time spent evaluating potentials: sum over potential-kernel launches
+                                (CUDA events, ENQUEUE driver), or the potential phases of the persistent
+                                kernel (its own %globaltimer stamps, FUSED driver); 0 with GRAPH     */
+    int32_t potential_launches; /* potential passes run (stand-alone launches, or phases of the one kernel) */
     int32_t launches;        /* all kernel launches issued by the run                    */
     int32_t passes;          /* loop passes executed (max over haloes)                   */
-    int32_t reserved;
+    int32_t driver;          /* HALMA_DRIVER_* that ran                                  */
     int64_t pairs;           /* interactions (target, source) summed over haloes and passes:
                                 what the reference's double loop visits                  */
     int64_t evaluations;     /* 1/r evaluations made for them: = pairs, or fewer with
                                 symmetric = 1 (one evaluation serves both particles)      */
+    double  loop_ms;         /* FUSED: duration of the persistent kernel by its own clock; else 0 */
+    double  comm_ms;         /* split mode: CUDA-event time of the NCCL collectives of the run   */
+    int64_t comm_bytes;      /* split mode: bytes handed to the collectives, all passes          */
+    double  phase_ms[5];     /* FUSED: the persistent kernel's time by phase: prologue (pack, first decisions,
+                                first ticket table), potential passes, energy + compaction, commit + ticket
+                                tables, epilogue (member lists)                                    */
 } halma_run_stats;
 
 /* offsets: int64[n_halo+1], ext_offsets[g]: int64[n_halo+1] for g < n_groups (host). */
@@ -321,6 +340,10 @@ int halma_snapshot_upload_particles(halma_snapshot *snap, int kind, int64_t n, c
                                     const double *z, const double *mass, const int64_t *id);
 int halma_snapshot_gather(halma_snapshot *snap, double cx, double cy, double cz, double R, double rho_B,
                           double mass_scale, double dm_heavy_min, int64_t *counts4);
+/* AMRgrid_to_particles alone (halo_gas.py:56-141; call site halo_properties.py:318): gas cells strictly inside
+ * the BOX [c - R, c + R]^3, no sphere test, no particles (counts4[1..3] = 0). */
+int halma_snapshot_gather_box(halma_snapshot *snap, double cx, double cy, double cz, double R, double rho_B,
+                              double mass_scale, int64_t *counts4);
 int halma_snapshot_fetch(halma_snapshot *snap, double *const *gas8, double *const *dm4, double *const *dml4,
                          double *const *st4, int64_t *st_id);
 int halma_snapshot_result_device(halma_snapshot *snap, double **ptr4, int64_t **st_id, int64_t *counts4);

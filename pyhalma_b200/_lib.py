@@ -16,6 +16,8 @@ HALMA_OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_ALIGN, ERR_TOO_LARGE, ERR_STATE, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7
 MODE_FAST, MODE_EXACT = 0, 1
 MAX_GROUPS = 4
+ABI_VERSION = 2
+DRIVER_AUTO, DRIVER_GRAPH, DRIVER_ENQUEUE, DRIVER_FUSED = 0, 1, 2, 3
 
 EXPORTS = (
     "halma_last_error", "halma_abi_version", "halma_device_count", "halma_device_info",
@@ -25,7 +27,7 @@ EXPORTS = (
     "halma_plan_run", "halma_plan_download", "halma_unbind_halo", "halma_microbench",
     "halma_halo_shape_f32", "halma_sigma_projections_f32",
     "halma_snapshot_create", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_snapshot_upload_patch",
-    "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_fetch", "halma_last_kernel_ms",
+    "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_gather_box", "halma_snapshot_fetch", "halma_last_kernel_ms",
     "halma_snapshot_result_device", "halma_snapshot_fetch_star", "halma_selftest_exact_arith",
     "halma_find_target_block",
 )
@@ -57,7 +59,9 @@ class HaloResult(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("potential_ms", C.c_double),
                 ("potential_launches", C.c_int32), ("launches", C.c_int32), ("passes", C.c_int32),
-                ("reserved", C.c_int32), ("pairs", C.c_int64), ("evaluations", C.c_int64)]
+                ("driver", C.c_int32), ("pairs", C.c_int64), ("evaluations", C.c_int64),
+                ("loop_ms", C.c_double), ("comm_ms", C.c_double), ("comm_bytes", C.c_int64),
+                ("phase_ms", C.c_double * 5)]
 
 
 _lib = None
@@ -113,6 +117,7 @@ def lib() -> C.CDLL:
     L.halma_snapshot_upload_patch.argtypes = [vp, i64] + [vp] * 7
     L.halma_snapshot_upload_particles.argtypes = [vp, i32, i64] + [vp] * 5
     L.halma_snapshot_gather.argtypes = [vp] + [C.c_double] * 7 + [vp]
+    L.halma_snapshot_gather_box.argtypes = [vp] + [C.c_double] * 6 + [vp]
     L.halma_snapshot_fetch.argtypes = [vp] * 6
     L.halma_snapshot_result_device.argtypes = [vp] * 4
     L.halma_snapshot_fetch_star.argtypes = [vp, i64, vp, vp]
@@ -125,7 +130,7 @@ def lib() -> C.CDLL:
                         "halma_comm_destroy", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_last_kernel_ms",
                         "halma_find_target_block"):
             fn.restype = i32
-    if L.halma_abi_version() != 1:
+    if L.halma_abi_version() != ABI_VERSION:
         raise ImportError("libhalma_unbind ABI version mismatch")
     _lib = L
     return L

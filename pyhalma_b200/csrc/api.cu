@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "fused.h"
 #include "loop_kernels.h"
 #include "potential.h"
 #include "sortprep.h"
@@ -84,6 +85,7 @@ static int get_ctx(int device, DeviceCtx **out)
         CU_TRY(potential_configure(HALMA_MODE_EXACT, 0, &c.bps_exact));
         for (int v = 0; v < potential_num_variants() && v < kMaxVariants; ++v)
             CU_TRY(potential_configure(HALMA_MODE_FAST, v, &c.bps_fast[v]));
+        CU_TRY(fused_configure());
         CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         CU_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -412,6 +414,8 @@ struct NcclApi {
     int (*CommInitRank)(void **, int, UID128, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 }  // namespace
@@ -435,6 +439,8 @@ static int load_nccl()
     g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
     g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
         return fail(HALMA_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
     g_nccl.handle = h;
@@ -483,7 +489,13 @@ struct halma_plan {
     // working sets
     DBuf<float> d_work;                   // 2 * 4 * n_pad
     DBuf<int32_t> d_widx;                 // 2 * n_pad
-    DBuf<int32_t> d_hint;                 // per-halo int arrays: 9 * n_halo + (n_halo + 1)
+    DBuf<int32_t> d_hint;                 // per-halo int arrays: 9 * n_halo + (n_halo + 1) + halo_done, halo_stamp
+    DBuf<int32_t> d_rank_of, d_range;     // position of a halo in `order`; min | max of x, y, z per halo (3 + 3 ints)
+    DBuf<int4> d_sched;                   // scheduling records, in `order` space
+    DBuf<double> d_phi_full;
+    int fused_index = -1;                 // persistent loop kernel serving this plan (fused.cu), -1: none
+    int driver_ran = HALMA_DRIVER_ENQUEUE;
+    std::vector<cudaEvent_t> cev;         // split mode: 2 per pass around the potential collectives, 2 around the rest
     DBuf<double> d_hdbl;                  // per-halo doubles: M(1) vb(3) vb_next(3) com(3)
     DBuf<unsigned long long> d_pairs, d_evals;
     DBuf<double> d_phi_sym, d_symq;
@@ -545,6 +557,7 @@ struct halma_plan {
         d_nsel.release(); d_keys.release(); d_ids.release(); d_skey.release(); d_ismem.release();
         d_sorttemp.release(); d_sf.release(); d_corr.release();
         d_phi_ext.release(); d_phi_keep.release(); d_rem.release(); d_reuse_int.release();
+        d_rank_of.release(); d_range.release(); d_sched.release(); d_phi_full.release();
     }
     ~halma_plan()
     {
@@ -554,6 +567,7 @@ struct halma_plan {
         if (stream) cudaStreamSynchronize(stream);
         if (comm && comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         for (auto e : ev) cudaEventDestroy(e);
+        for (auto e : cev) cudaEventDestroy(e);
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_stop) cudaEventDestroy(ev_stop);
         if (h_flags) cudaFreeHost(h_flags);
@@ -661,7 +675,13 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(P->d_chunk_halo.alloc(chunk_halo.size()));
     CU_TRY(P->d_chunk_p0.alloc(chunk_p0.size()));
     CU_TRY(P->d_order.alloc(nh));
+    CU_TRY(P->d_rank_of.alloc(nh));
+    CU_TRY(P->d_sched.alloc(nh));
+    CU_TRY(P->d_range.alloc(6 * nh));
+    std::vector<int32_t> rank_of(nh);
+    for (int64_t k = 0; k < nh; ++k) rank_of[order[k]] = static_cast<int32_t>(k);
     if (nh) {
+        CU_TRY(cudaMemcpyAsync(P->d_rank_of.p, rank_of.data(), nh * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemcpyAsync(P->d_halo.p, halo.data(), nh * sizeof(HaloDesc), cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemcpyAsync(P->d_order.p, order.data(), nh * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     }
@@ -685,7 +705,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(P->d_vb_user.alloc(3 * nh));
     CU_TRY(P->d_work.alloc(8 * NP));
     CU_TRY(P->d_widx.alloc(2 * NP));
-    CU_TRY(P->d_hint.alloc(9 * nh + nh + 1));
+    CU_TRY(P->d_hint.alloc(12 * nh + 1));
     CU_TRY(P->d_hdbl.alloc(10 * nh));
     CU_TRY(P->d_pairs.alloc(nh));
     CU_TRY(P->d_evals.alloc(nh));
@@ -741,8 +761,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(cudaMemsetAsync(P->d_ext.p, 0, 4 * static_cast<size_t>(P->n_ext_pad) * sizeof(float), s));
     CU_TRY(cudaMemsetAsync(P->d_vb_user.p, 0, 3 * nh * sizeof(double), s));
     CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&P->h_flags), sizeof(int32_t) * (cfg.max_iter + 1)));
-    P->ev.resize(3 * static_cast<size_t>(cfg.max_iter));
-    for (auto &e : P->ev) CU_TRY(cudaEventCreate(&e));
+    // events of the multi-launch drivers are created on first use (plan_run)
     CU_TRY(cudaEventCreate(&P->ev_start));
     CU_TRY(cudaEventCreate(&P->ev_stop));
 
@@ -783,6 +802,12 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.nsplit = hi + 6 * nh;
     L.converged = hi + 7 * nh;
     L.item_base = hi + 9 * nh;       // n_halo + 1 entries (slot 8 is spare)
+    L.halo_done = hi + 10 * nh + 1;
+    L.halo_stamp = hi + 11 * nh + 1;
+    L.rank_of = P->d_rank_of.p;
+    L.sched = P->d_sched.p;
+    L.halo_rmin = P->d_range.p;
+    L.halo_rmax = P->d_range.p + 3 * nh;
     double *hd = P->d_hdbl.p;
     L.hM = hd;
     L.hvb = hd + nh;
@@ -828,10 +853,13 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.max_split = planes;
     L.halo_redo = P->d_redo.p;
     L.np_enabled = P->np ? 1 : 0;
+    L.redo_enabled = 0;      // set below, once the reuse options are known
     for (int a = 0; a < 3 && P->np; ++a) {
         const SortedAxisMut &A = P->sax[a];
         L.ax[a] = SortedAxis{A.x, A.y, A.z, A.m, A.key, A.slot, A.tgt, A.inv, A.corr};
+        L.ax_m0[a] = A.m0;
     }
+    L.n_spad = P->np ? P->n_spad : 0;
     // symmetric self-term: rides on the predicate-free kernel's throughput shape (128-member tiles)
     P->sym = cfg.symmetric && P->np && P->variant == 0 && potential_group_size(cfg.mode, P->variant) == 128;
     if (P->sym) {
@@ -847,18 +875,20 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     // Split mode: incremental passes need nothing extra -- their main tickets are dealt to the ranks and
     // all-reduced like any others and kernels 2-3, which keep the sums, run replicated; the external-sum
     // planes would need an all-reduce of their own in the first pass, so the cache stays off there.
-    P->cache_ext = cfg.cache_external && P->np && cfg.n_ranks == 1 && P->max_ext > 0;
-    P->incr = cfg.incremental && P->np;
+    P->cache_ext = cfg.cache_external && cfg.mode == HALMA_MODE_FAST && P->max_ext > 0;
+    P->incr = cfg.incremental && cfg.mode == HALMA_MODE_FAST;
     if (P->cache_ext || P->incr) CU_TRY(P->d_reuse_int.alloc(3 * std::max<size_t>(nh, 1)));
     if (P->cache_ext) CU_TRY(P->d_phi_ext.alloc(planes * NP));
     if (P->incr) {
         CU_TRY(P->d_phi_keep.alloc(NP));
+        CU_TRY(P->d_phi_full.alloc(NP));
         CU_TRY(P->d_rem.alloc(4 * NP));
     }
     L.phi_ext = P->d_phi_ext.p;
     L.ext_ok = P->d_reuse_int.p;
     L.cache_ext = P->cache_ext ? 1 : 0;
     L.phi_keep = P->d_phi_keep.p;
+    L.phi_full = P->d_phi_full.p;
     L.rx = P->d_rem.p;
     L.ry = P->incr ? P->d_rem.p + NP : nullptr;
     L.rz = P->incr ? P->d_rem.p + 2 * NP : nullptr;
@@ -866,6 +896,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.incr = P->d_reuse_int.p ? P->d_reuse_int.p + nh : nullptr;
     L.rem_cnt = P->d_reuse_int.p ? P->d_reuse_int.p + 2 * nh : nullptr;
     L.incr_enabled = P->incr ? 1 : 0;
+    L.redo_enabled = (P->np || P->incr) ? 1 : 0;
 
     PotParams &Q = P->pp;
     memset(&Q, 0, sizeof Q);
@@ -904,11 +935,16 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     Q.widx[0] = L.widx[0];
     Q.widx[1] = L.widx[1];
     Q.phi_keep = L.phi_keep;
+    Q.phi_full = L.phi_full;
     Q.src[6] = F32Set{L.rx, L.ry, L.rz, L.rm};
     for (int a = 0; a < 3 && P->np; ++a) {
         Q.ax[a] = L.ax[a];
         Q.src[3 + a] = F32Set{P->sax[a].x, P->sax[a].y, P->sax[a].z, P->sax[a].m};
     }
+    // the persistent loop kernel, where one exists for this configuration (fused.cu)
+    P->fused_index = cfg.n_ranks == 1 ? fused_kernel_index(cfg.mode, P->variant, P->np, P->sym) : -1;
+    if (cfg.use_graph == HALMA_DRIVER_FUSED && P->fused_index < 0)
+        return fail(HALMA_ERR_INVALID, "no persistent loop kernel for this plan (split mode or a tuning kernel shape)");
     CU_TRY(cudaStreamSynchronize(s));
     return HALMA_OK;
 }
@@ -1121,23 +1157,21 @@ extern "C" int halma_plan_use_comm(halma_plan *P, halma_comm *comm)
     return HALMA_OK;
 }
 
-// Kernels of one pass, without events or host copies (shared by both loop drivers).
+// Kernels of one pass, without events or host copies (graph driver).
 static int enqueue_pass_kernels(halma_plan *P, const LoopParams &lp)
 {
     cudaStream_t s = P->stream;
     const int sm = P->ctx->sm_count;
     const int grid = sm * P->ctx->blocks(P->cfg.mode, P->variant);
-    if (P->sym) CU_TRY(cudaMemsetAsync(P->d_phi_sym.p, 0, static_cast<size_t>(P->n_pad) * sizeof(double), s));
     CU_TRY(potential_launch(P->pp, P->cfg.mode, P->variant, grid, s));
-    if (P->np) {
+    if (P->lp.redo_enabled) {
         PotParams redo = P->pp;
         redo.redo_only = 1;
         CU_TRY(potential_launch(redo, P->cfg.mode, P->variant, grid, s));
     }
     CU_TRY(launch_energy_flag(lp, sm, s));
-    CU_TRY(launch_halo_decide(lp, 0, sm, s));
     CU_TRY(launch_compact(lp, sm, s));
-    CU_TRY(launch_schedule(lp, 0, s));
+    CU_TRY(launch_schedule(lp, 0, sm, s));
     return HALMA_OK;
 }
 
@@ -1178,54 +1212,90 @@ static int plan_build_graph(halma_plan *P)
     return HALMA_OK;
 }
 
-static int enqueue_pass(halma_plan *P, int pass)
+// One pass of the enqueue-ahead driver (the only driver of split mode).  Split mode: the ranks evaluate
+// disjoint target groups; what the replicated kernels 2-3 need of the others' results is exchanged by
+// all-reduces on the plan's stream, in which every element is written by one rank and the others add
+// exact zeros (the two-sided sums: exact additions of quantised addends), so the outcome is bit-identical
+// to the single-GPU run.  *comm_bytes counts what went through the collectives.
+static int enqueue_pass(halma_plan *P, int pass, int64_t *comm_bytes)
 {
     cudaStream_t s = P->stream;
     const int sm = P->ctx->sm_count;
     const int grid = sm * P->ctx->blocks(P->cfg.mode, P->variant);
+    const bool split = P->cfg.n_ranks > 1;
+    const size_t NP = static_cast<size_t>(P->n_pad);
     CU_TRY(cudaEventRecord(P->ev[3 * pass], s));
-    if (P->np && P->cfg.n_ranks > 1)      // split mode: every correction entry is written by one rank only
-        CU_TRY(cudaMemsetAsync(P->d_corr.p, 0, 3 * static_cast<size_t>(P->n_pad) * sizeof(double), s));
-    if (P->sym) CU_TRY(cudaMemsetAsync(P->d_phi_sym.p, 0, static_cast<size_t>(P->n_pad) * sizeof(double), s));
+    if (P->np && split)      // split mode: every correction entry is written by one rank only
+        CU_TRY(cudaMemsetAsync(P->d_corr.p, 0, 3 * NP * sizeof(double), s));
     CU_TRY(potential_launch(P->pp, P->cfg.mode, P->variant, grid, s));
-    if (P->np) {
-        // haloes whose predicate-free sums came out non-finite are recomputed with the predicate
-        if (P->cfg.n_ranks > 1) {
+    if (P->lp.redo_enabled) {
+        // haloes whose predicate-free sums came out non-finite (or whose incremental pass removed too much of
+        // a member's potential) are recomputed with the predicate
+        if (split) {
             // split mode: every rank must take the same decision
+            CU_TRY(cudaEventRecord(P->cev[4 * pass], s));
             int e = g_nccl.AllReduce(P->d_redo.p, P->d_redo.p, static_cast<size_t>(P->n_halo), /*ncclInt32*/ 2,
                                      /*ncclMax*/ 2, P->comm, s);
             if (e) return nccl_fail(e, "ncclAllReduce(flags)");
             CU_TRY(launch_sync_redo(P->lp, s));
-            e = g_nccl.AllReduce(P->d_corr.p, P->d_corr.p, 3 * static_cast<size_t>(P->n_pad), /*ncclFloat64*/ 8,
-                                 /*ncclSum*/ 0, P->comm, s);
-            if (e) return nccl_fail(e, "ncclAllReduce(corrections)");
+            CU_TRY(cudaEventRecord(P->cev[4 * pass + 1], s));
+            *comm_bytes += static_cast<int64_t>(P->n_halo) * 4;
         }
         PotParams redo = P->pp;
         redo.redo_only = 1;
         CU_TRY(potential_launch(redo, P->cfg.mode, P->variant, grid, s));
     }
     CU_TRY(cudaEventRecord(P->ev[3 * pass + 1], s));
-    if (P->cfg.n_ranks > 1) {
+    if (split) {
         CU_TRY(launch_fold_partials(P->lp, sm, s));
-        int e = g_nccl.AllReduce(P->d_phi.p, P->d_phi.p, static_cast<size_t>(P->n_pad), /*ncclFloat64*/ 8,
-                                 /*ncclSum*/ 0, P->comm, s);
-        if (e) return nccl_fail(e, "ncclAllReduce");
-        if (P->sym) {
+        CU_TRY(cudaEventRecord(P->cev[4 * pass + 2], s));
+        // one group = one fused NCCL launch for everything kernels 2-3 need
+        if (g_nccl.GroupStart) g_nccl.GroupStart();
+        int e = g_nccl.AllReduce(P->d_phi.p, P->d_phi.p, NP, /*ncclFloat64*/ 8, /*ncclSum*/ 0, P->comm, s);
+        *comm_bytes += NP * 8;
+        if (!e && P->np) {
+            e = g_nccl.AllReduce(P->d_corr.p, P->d_corr.p, 3 * NP, 8, 0, P->comm, s);
+            *comm_bytes += 3 * NP * 8;
+        }
+        if (!e && P->sym) {
             // every rank summed the two-sided terms of its row tiles; the addends are multiples of the
             // halo's quantum and the totals stay inside the exact window, so this sum is exact too
-            e = g_nccl.AllReduce(P->d_phi_sym.p, P->d_phi_sym.p, static_cast<size_t>(P->n_pad), /*ncclFloat64*/ 8,
-                                 /*ncclSum*/ 0, P->comm, s);
-            if (e) return nccl_fail(e, "ncclAllReduce(symmetric sums)");
+            e = g_nccl.AllReduce(P->d_phi_sym.p, P->d_phi_sym.p, NP, 8, 0, P->comm, s);
+            *comm_bytes += NP * 8;
         }
+        if (!e && P->cache_ext && pass == 0) {
+            // external-sum cache: the sums over the fixed external sources are exchanged once per run
+            e = g_nccl.AllReduce(P->d_phi_ext.p, P->d_phi_ext.p, NP, 8, 0, P->comm, s);
+            *comm_bytes += NP * 8;
+        }
+        if (g_nccl.GroupEnd) {
+            const int e2 = g_nccl.GroupEnd();
+            if (!e) e = e2;
+        }
+        if (e) return nccl_fail(e, "ncclAllReduce");
+        CU_TRY(cudaEventRecord(P->cev[4 * pass + 3], s));
         CU_TRY(launch_set_nsplit_one(P->lp, s));
     }
     CU_TRY(launch_energy_flag(P->lp, sm, s));
-    CU_TRY(launch_halo_decide(P->lp, 0, sm, s));
     CU_TRY(launch_compact(P->lp, sm, s));
-    CU_TRY(launch_schedule(P->lp, 0, s));
+    CU_TRY(launch_schedule(P->lp, 0, sm, s));
     CU_TRY(cudaMemcpyAsync(&P->h_flags[pass], &P->d_st.p->any_active, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaEventRecord(P->ev[3 * pass + 2], s));
     return HALMA_OK;
+}
+
+static int pick_driver(const halma_plan *P)
+{
+    int d = P->cfg.use_graph;
+    if (d == HALMA_DRIVER_AUTO) {
+        if (const char *e = getenv("HALMA_DRIVER")) {      // fused | enqueue | graph: tuning and A/B tests
+            if (!strcmp(e, "enqueue")) d = HALMA_DRIVER_ENQUEUE;
+            else if (!strcmp(e, "graph")) d = HALMA_DRIVER_GRAPH;
+        }
+    }
+    if (P->cfg.n_ranks > 1) return HALMA_DRIVER_ENQUEUE;
+    if (d == HALMA_DRIVER_AUTO || d == HALMA_DRIVER_FUSED) return P->fused_index >= 0 ? HALMA_DRIVER_FUSED : HALMA_DRIVER_ENQUEUE;
+    return d;
 }
 
 extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
@@ -1239,25 +1309,55 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
     CU_TRY(cudaSetDevice(P->cfg.device));
     cudaStream_t s = P->stream;
     const int sm = P->ctx->sm_count;
-    const size_t NU = static_cast<size_t>(P->n_user);
     const int nh = static_cast<int>(P->n_halo);
+    const int driver = pick_driver(P);
     int launches = 0, pot_launches = 0, passes = 0;
-    bool graph_run = false;
+    int64_t comm_bytes = 0;
+    LoopState hst;
+    memset(&hst, 0, sizeof hst);
 
+    if (driver != HALMA_DRIVER_FUSED && P->ev.empty()) {
+        P->ev.resize(3 * static_cast<size_t>(P->cfg.max_iter));
+        for (auto &e : P->ev) CU_TRY(cudaEventCreate(&e));
+        if (P->cfg.n_ranks > 1) {
+            P->cev.resize(4 * static_cast<size_t>(P->cfg.max_iter));
+            for (auto &e : P->cev) CU_TRY(cudaEventCreate(&e));
+        }
+    }
     CU_TRY(cudaEventRecord(P->ev_start, s));
+    // every member is evaluated by the first pass, which writes its mask / be / E: no need to clear them
     CU_TRY(cudaMemsetAsync(P->d_st.p, 0, sizeof(LoopState), s));
-    CU_TRY(cudaMemsetAsync(P->d_mask.p, 0, NU, s));
-    CU_TRY(cudaMemsetAsync(P->d_be.p, 0, NU * sizeof(float), s));
-    CU_TRY(cudaMemsetAsync(P->d_E.p, 0, NU * sizeof(double), s));
     CU_TRY(cudaMemsetAsync(P->d_hint.p, 0, P->d_hint.n * sizeof(int32_t), s));
+    if (P->sym && nh) {
+        CU_TRY(cudaMemsetAsync(P->d_phi_sym.p, 0, static_cast<size_t>(P->n_pad) * sizeof(double), s));
+        CU_TRY(cudaMemsetAsync(P->d_range.p, 0x7f, 3 * nh * sizeof(int32_t), s));
+        CU_TRY(cudaMemsetAsync(P->d_range.p + 3 * nh, 0x80, 3 * nh * sizeof(int32_t), s));
+    }
     if (P->cfg.vb_fixed && nh)
         CU_TRY(cudaMemcpyAsync(P->lp.hvb, P->d_vb_user.p, 3 * nh * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    if (nh > 0) {
+    if (nh > 0 && driver == HALMA_DRIVER_FUSED) {
+        // the whole loop in one persistent kernel; the pack runs inside it unless the sorted copies have to
+        // be (re)built from the packed members first
+        int do_pack = 1;
+        if (P->np && P->sorted_dirty) {
+            CU_TRY(launch_pack_members(P->lp, sm, s));
+            ++launches;
+            if (int rc = plan_prepare_sorted(P)) return rc;
+            do_pack = 0;
+            if (P->sym) {      // the pack's coordinate ranges are kept; nothing else to reset
+            }
+        }
+        CU_TRY(fused_launch(P->fused_index, P->pp, P->lp, do_pack, sm, s));
+        ++launches;
+        CU_TRY(cudaMemcpyAsync(&hst, P->d_st.p, sizeof hst, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaEventRecord(P->ev_stop, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        passes = pot_launches = hst.pass;
+    } else if (nh > 0) {
         CU_TRY(launch_pack_members(P->lp, sm, s));
-        if (P->sym) CU_TRY(launch_halo_extent(P->lp, s));
         if (int rc = plan_prepare_sorted(P)) return rc;
-        CU_TRY(launch_halo_decide(P->lp, 1, sm, s));
-        CU_TRY(launch_schedule(P->lp, 1, s));
+        CU_TRY(launch_halo_decide_init(P->lp, sm, s));
+        CU_TRY(launch_schedule(P->lp, 1, sm, s));
         launches += 3;
         // Enqueue passes ahead of the device; a pinned flag written at the end of each pass
         // tells the host when the loop has converged.  The device never waits for the host:
@@ -1267,13 +1367,11 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         const int max_iter = P->cfg.max_iter;
         int queued = 0;
         bool done = false;
-        graph_run = P->cfg.use_graph && P->cfg.n_ranks == 1;
-        if (graph_run) {
+        if (driver == HALMA_DRIVER_GRAPH) {
             // graph driver: every pass inside one launch, convergence decided on the device
             if (P->graph_dirty)
                 if (int rc = plan_build_graph(P)) return rc;
             CU_TRY(cudaGraphLaunch(P->gexec, s));
-            LoopState hst;
             CU_TRY(cudaMemcpyAsync(&hst, P->d_st.p, sizeof hst, cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
             passes = hst.pass;
@@ -1282,7 +1380,7 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         }
         while (!done) {
             while (queued < max_iter && queued < passes + kAhead) {
-                if (int rc = enqueue_pass(P, queued)) return rc;
+                if (int rc = enqueue_pass(P, queued, &comm_bytes)) return rc;
                 ++queued;
             }
             if (passes >= queued) break;
@@ -1291,28 +1389,50 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
             ++passes;
             if (!still) done = true;
         }
-        launches += queued * (5 + (P->cfg.n_ranks > 1 ? 2 : 0) + (P->np ? (P->cfg.n_ranks > 1 ? 2 : 1) : 0));
+        launches += queued * (4 + (P->cfg.n_ranks > 1 ? 2 : 0) + (P->lp.redo_enabled ? (P->cfg.n_ranks > 1 ? 2 : 1) : 0));
         pot_launches = queued;
         CU_TRY(launch_finalize(P->lp, sm, s));
         ++launches;
+        CU_TRY(cudaEventRecord(P->ev_stop, s));
+        CU_TRY(cudaStreamSynchronize(s));
+    } else {
+        CU_TRY(cudaEventRecord(P->ev_stop, s));
+        CU_TRY(cudaStreamSynchronize(s));
     }
-    CU_TRY(cudaEventRecord(P->ev_stop, s));
-    CU_TRY(cudaStreamSynchronize(s));
     P->ran = true;
+    P->driver_ran = driver;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, P->ev_start, P->ev_stop));
         stats->total_ms = ms;
-        double pot = 0.0;      // per-launch events exist only with the enqueue-ahead driver
-        for (int k = 0; k < pot_launches && !graph_run; ++k) {
-            CU_TRY(cudaEventElapsedTime(&ms, P->ev[3 * k], P->ev[3 * k + 1]));
-            pot += ms;
+        double pot = 0.0, comm = 0.0;
+        if (driver == HALMA_DRIVER_FUSED) {
+            pot = hst.pot_ns * 1e-6;
+            stats->loop_ms = hst.loop_ns * 1e-6;
+            for (int k = 0; k < 5; ++k) stats->phase_ms[k] = hst.phase_ns[k] * 1e-6;
+        } else if (driver == HALMA_DRIVER_ENQUEUE) {      // per-launch events exist only with the enqueue-ahead driver
+            for (int k = 0; k < pot_launches; ++k) {
+                CU_TRY(cudaEventElapsedTime(&ms, P->ev[3 * k], P->ev[3 * k + 1]));
+                pot += ms;
+                if (P->cfg.n_ranks > 1) {
+                    if (P->lp.redo_enabled) {
+                        CU_TRY(cudaEventElapsedTime(&ms, P->cev[4 * k], P->cev[4 * k + 1]));
+                        comm += ms;
+                        pot -= ms;      // the flag exchange sits between the two potential launches
+                    }
+                    CU_TRY(cudaEventElapsedTime(&ms, P->cev[4 * k + 2], P->cev[4 * k + 3]));
+                    comm += ms;
+                }
+            }
         }
         stats->potential_ms = pot;
+        stats->comm_ms = comm;
+        stats->comm_bytes = comm_bytes;
         stats->potential_launches = pot_launches;
         stats->launches = launches;
         stats->passes = passes;
+        stats->driver = driver;
         if (nh) {
             std::vector<unsigned long long> pr(nh);
             CU_TRY(cudaMemcpy(pr.data(), P->d_pairs.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

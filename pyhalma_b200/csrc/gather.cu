@@ -58,6 +58,7 @@ struct Query {
     double box[6];               // cx-R, cx+R, cy-R, cy+R, cz-R, cz+R   (halo_gas.py:87-88)
     double cx, cy, cz, R, R2;
     double mass_factor[2];       // rho_B, rete^3
+    int box_only;                // gas: the box test alone (AMRgrid_to_particles, halo_gas.py:56-141)
 };
 
 // One thread per patch: the index range of the cells whose centres can lie strictly inside
@@ -146,7 +147,7 @@ struct CellSel {
         // :216-218, :236  sqrt((x-cx)^2 + (y-cy)^2 + (z-cz)^2) < R
         const double dx = __dsub_rn(it.x, q.cx), dy = __dsub_rn(it.y, q.cy), dz = __dsub_rn(it.z, q.cz);
         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        return __dsqrt_rn(d2) < q.R;
+        return q.box_only || __dsqrt_rn(d2) < q.R;
     }
     __device__ __forceinline__ void emit(const Item &it, int64_t o) const
     {
@@ -781,8 +782,25 @@ extern "C" int halma_snapshot_upload_particles(halma_snapshot *s, int kind, int6
     return build_index(s, kind);
 }
 
+static int snapshot_gather(halma_snapshot *s, double cx, double cy, double cz, double R, double rho_B,
+                           double mass_scale, double dm_heavy_min, int64_t *counts4, bool box_only);
+
 extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, double cz, double R, double rho_B,
                                      double mass_scale, double dm_heavy_min, int64_t *counts4)
+{
+    return snapshot_gather(s, cx, cy, cz, R, rho_B, mass_scale, dm_heavy_min, counts4, false);
+}
+
+// AMRgrid_to_particles on its own (halo_gas.py:56-141, called at halo_properties.py:318): the gas cells whose
+// centres lie strictly inside the BOX of half-width R, without the sphere test; no particles are selected.
+extern "C" int halma_snapshot_gather_box(halma_snapshot *s, double cx, double cy, double cz, double R, double rho_B,
+                                         double mass_scale, int64_t *counts4)
+{
+    return snapshot_gather(s, cx, cy, cz, R, rho_B, mass_scale, -std::numeric_limits<double>::infinity(), counts4, true);
+}
+
+static int snapshot_gather(halma_snapshot *s, double cx, double cy, double cz, double R, double rho_B,
+                           double mass_scale, double dm_heavy_min, int64_t *counts4, bool box_only)
 {
     if (!s || !counts4) return halma_internal_fail(HALMA_ERR_INVALID, "null pointer");
     if (dm_heavy_min != dm_heavy_min) return halma_internal_fail(HALMA_ERR_INVALID, "dm_heavy_min is NaN");
@@ -797,6 +815,7 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
     q.R2 = R * R;
     q.mass_factor[0] = rho_B;
     q.mass_factor[1] = mass_scale;
+    q.box_only = box_only ? 1 : 0;
     KernelTimer timer(s->stream);
     // ---- gas cells ----
     if (s->pd_dirty) {
@@ -843,7 +862,7 @@ extern "C" int halma_snapshot_gather(halma_snapshot *s, double cx, double cy, do
     // ---- DM (one or two species) and stars ----
     const double inf = std::numeric_limits<double>::infinity();
     const bool split = dm_heavy_min > -inf;
-    for (int sel_id = 1; sel_id < 4; ++sel_id) {
+    for (int sel_id = 1; sel_id < 4 && !box_only; ++sel_id) {
         if (sel_id == 2 && !split) continue;
         const int kind = sel_id == 3 ? 1 : 0;
         const int64_t n = s->n_part[kind];

@@ -25,7 +25,14 @@ struct LoopParams {
     float *wx[2], *wy[2], *wz[2], *wm[2];
     int32_t *widx[2];
     // per-halo dynamic state
-    int32_t *cnt, *cnt_next, *iter, *active, *active_next, *halo_buf, *nsplit, *item_base, *converged;
+    int32_t *cnt, *cnt_next, *iter, *active, *active_next, *halo_buf, *item_base, *converged;
+    int32_t *nsplit;                      // [n_halo] j-splits of the coming pass, in `order` space like item_base
+    const int32_t *rank_of;               // [n_halo] position of a halo in `order`
+    int4 *sched;                          // [n_halo] scheduling record per halo, in `order` space (decide_halo)
+    int32_t *halo_done;                   // [n_halo] chunks of the halo finished by the energy step of this pass
+    int32_t *halo_stamp;                  // [n_halo] pass + 1 once the halo's decision of that pass is published
+    int32_t *halo_rmin, *halo_rmax;       // [3 n_halo] min / max of x, y, z as order-preserving ints (pack);
+                                          // set to 0x7f7f7f7f / 0x80808080 before the pack
     double *hM, *hvb, *hvb_next, *hcom;
     unsigned long long *pairs;
     unsigned long long *evals;            // per halo: 1/r evaluations actually made (< pairs in symmetric mode)
@@ -51,10 +58,13 @@ struct LoopParams {
     int32_t vb_fixed, max_iter, mode, group_size, rank, n_ranks, target_items, max_split;
     // predicate-free FAST path (potential.cu): sorted copies + per-halo fallback flags
     SortedAxis ax[3];
+    const float *ax_m0[3];                // pristine masses of the sorted copies
+    int64_t n_spad;                       // length of one sorted copy
     int32_t *halo_redo;
     int32_t np_enabled;
+    int32_t redo_enabled;                 // some pass may hand a halo to the predicated re-evaluation (halo_redo)
     // symmetric self-term (potential.cu::sym_ticket): off-diagonal member x member sums
-    const double *phi_sym;                // [n_pad]
+    double *phi_sym;                      // [n_pad]; the energy step clears what it read
     int32_t sym_enabled;
     double *sym_ext;                      // [n_halo] largest coordinate extent of the halo's members
     double *sym_q;                        // [n_halo] quantum of the symmetric sums for the coming pass
@@ -64,6 +74,7 @@ struct LoopParams {
     int32_t cache_ext;
     // incremental passes: the complete float64 potential of the previous pass, members it removed
     double *phi_keep;                     // [n_pad] by original slot
+    double *phi_full;                     // [n_pad] by original slot: the potential of the last FULL pass
     float *rx, *ry, *rz, *rm;             // [n_pad] removed members of the last pass, per halo at poff
     int32_t *rem_cnt;                     // [n_halo]
     int32_t *incr;                        // [n_halo] the coming / current pass of the halo is incremental
@@ -73,14 +84,13 @@ struct LoopParams {
 };
 
 cudaError_t launch_pack_members(const LoopParams &p, int sm_count, cudaStream_t s);
-cudaError_t launch_halo_extent(const LoopParams &p, cudaStream_t s);
 cudaError_t launch_pack_group(const HaloDesc *halo, int n_halo, int seg_index, int max_count,
                               const int64_t *ext_off, const double *m, const double *x, const double *y,
                               const double *z, float *em, float *ex, float *ey, float *ez, cudaStream_t s);
 cudaError_t launch_energy_flag(const LoopParams &p, int sm_count, cudaStream_t s);
-cudaError_t launch_halo_decide(const LoopParams &p, int init, int sm_count, cudaStream_t s);
+cudaError_t launch_halo_decide_init(const LoopParams &p, int sm_count, cudaStream_t s);
 cudaError_t launch_compact(const LoopParams &p, int sm_count, cudaStream_t s);
-cudaError_t launch_schedule(const LoopParams &p, int init, cudaStream_t s);
+cudaError_t launch_schedule(const LoopParams &p, int init, int sm_count, cudaStream_t s);
 cudaError_t launch_fold_partials(const LoopParams &p, int sm_count, cudaStream_t s);
 cudaError_t launch_sync_redo(const LoopParams &p, cudaStream_t s);
 cudaError_t launch_set_nsplit_one(const LoopParams &p, cudaStream_t s);

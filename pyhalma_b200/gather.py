@@ -99,6 +99,19 @@ class Snapshot:
                                                  float(rete) ** 3, float(dm_heavy_min), counts))
         return tuple(int(c) for c in counts)
 
+    def gather_box(self, cx, cy, cz, R, rho_B, rete=1.0):
+        """AMRgrid_to_particles (halo_gas.py:56-141): the 8 gas arrays of the cells strictly inside the box of
+        half-width R (no sphere test), as host arrays in the reference's order."""
+        counts = (C.c_int64 * 4)()
+        _lib.check(self._L.halma_snapshot_gather_box(self._h, float(cx), float(cy), float(cz), float(R), float(rho_B),
+                                                     float(rete) ** 3, counts))
+        ng = int(counts[0])
+        g = [np.empty(ng) for _ in range(8)]
+        if ng:
+            _lib.check(self._L.halma_snapshot_fetch(self._h, (C.c_void_p * 8)(*[a.ctypes.data for a in g]), None, None,
+                                                    None, None))
+        return tuple(g)
+
     def gather(self, cx, cy, cz, R, rho_B, rete=1.0, *, gas=True, dm=True, stars=True):
         """Returns the 17-tuple of st_gas_dm_particles_inside (halo_gas.py:276-277) as host arrays;
         classes that are switched off come back empty."""
@@ -180,26 +193,41 @@ class DeviceGather:
 
 # The reference passes the same snapshot objects for every halo of a snapshot (pyHALMA.py:930-1037);
 # keep the device copy of the last one seen.  The strong references keep id() from being reused.
-_cache: dict = {"key": None, "refs": None, "snap": None}
+_cache: dict = {"gas": None, "full": None}
 
 
 def snapshot_for(L, ncoarse, grid_data, gas_data, masclet_dm_data, masclet_st_data, mass_to_sun, device) -> Snapshot:
-    key = (id(grid_data), id(gas_data), id(masclet_dm_data), id(masclet_st_data), float(L), int(ncoarse),
-           float(mass_to_sun), int(device))
-    if _cache["key"] != key:
-        if _cache["snap"] is not None:
-            _cache["snap"].close()
-        _cache.update(key=None, refs=None, snap=None)
-        snap = Snapshot(L, ncoarse, grid_data, gas_data, masclet_dm_data, masclet_st_data, mass_to_sun=mass_to_sun,
-                        device=device)
-        _cache.update(key=key, refs=(grid_data, gas_data, masclet_dm_data, masclet_st_data), snap=snap)
-    return _cache["snap"]
+    """Device copy of the snapshot these objects describe.  Two slots: the grid + gas fields alone
+    (AMRgrid_to_particles passes no particles) and grid + gas + particles; a request without particles is also
+    served by the copy that has them, so alternating the two kinds of call per halo uploads nothing twice.
+    A replaced snapshot is dropped, not closed: DeviceGather handles hold a reference, and the device memory goes
+    when the last one does."""
+    gkey = (id(grid_data), id(gas_data), float(L), int(ncoarse), int(device))
+    want_particles = masclet_dm_data is not None or masclet_st_data is not None
+    full = _cache["full"]
+    if full is not None and full[0] == gkey and (not want_particles or full[1] == (
+            id(masclet_dm_data), id(masclet_st_data), float(mass_to_sun))):
+        return full[3]
+    if not want_particles:
+        gas = _cache["gas"]
+        if gas is None or gas[0] != gkey:
+            snap = Snapshot(L, ncoarse, grid_data, gas_data, None, None, device=device)
+            _cache["gas"] = gas = (gkey, None, (grid_data, gas_data), snap)
+        return gas[3]
+    snap = Snapshot(L, ncoarse, grid_data, gas_data, masclet_dm_data, masclet_st_data, mass_to_sun=mass_to_sun,
+                    device=device)
+    _cache["full"] = (gkey, (id(masclet_dm_data), id(masclet_st_data), float(mass_to_sun)),
+                      (grid_data, gas_data, masclet_dm_data, masclet_st_data), snap)
+    if _cache["gas"] is not None and _cache["gas"][0] == gkey:
+        _cache["gas"] = None          # the full copy serves those requests from now on
+    return snap
 
 
 def release_cached_snapshot() -> None:
-    if _cache["snap"] is not None:
-        _cache["snap"].close()
-    _cache.update(key=None, refs=None, snap=None)
+    for k in ("gas", "full"):
+        if _cache[k] is not None:
+            _cache[k][3].close()
+        _cache[k] = None
 
 
 def default_mass_to_sun() -> float:

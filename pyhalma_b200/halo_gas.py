@@ -185,13 +185,8 @@ def AMRgrid_to_particles(L, ncoarse, grid_data, gas_data, Rrps, cx, cy, cz, rho_
 
 
 def _box_gas(snap, cx, cy, cz, Rrps, rho_B):
-    # the device selects box AND sphere (:236 follows :233 at the only call site); the box alone is
-    # inside the sphere of radius sqrt(3)*Rrps, so ask for a slightly larger sphere and clip to the box here
-    out = snap.gather(cx, cy, cz, Rrps * 1.75, rho_B, 1.0, dm=False, stars=False)[:8]
-    x, y, z = out[0], out[1], out[2]
-    keep = ((x > cx - Rrps) & (x < cx + Rrps) & (y > cy - Rrps) & (y < cy + Rrps) & (z > cz - Rrps)
-            & (z < cz + Rrps))
-    return tuple(a[keep] for a in out)
+    # the box selection alone, made on the device (halma_snapshot_gather_box)
+    return snap.gather_box(cx, cy, cz, Rrps, rho_B, 1.0)
 
 
 def parallel_inside(array_x, array_y, array_z, R, cx, cy, cz):

@@ -37,7 +37,7 @@ def CM_velocity(M, part_list, st_vx, st_vy, st_vz, st_mass):  # noqa: N802
     return 0., 0., 0.
 
 
-def escape_velocity_unbinding(gas, stars, dm, vb, factor_v, *, max_iter=1, recompute_vb=False, mode="fast",
+def escape_velocity_unbinding(gas, stars, dm, vb, factor_v, *, max_iter=1, recompute_vb=False, mode=None,
                               device=0):
     """gas / dm = (x, y, z, mass); stars = (x, y, z, vx, vy, vz, mass); vb = bulk velocity.
 
@@ -54,10 +54,14 @@ def escape_velocity_unbinding(gas, stars, dm, vb, factor_v, *, max_iter=1, recom
 
 def escape_velocity_unbinding_fortran(rete, L, ncoarse, grid_data, gas_data, masclet_dm_data, cx, cy, cz,
                                       vx, vy, vz, Rmax, part_list, st_x, st_y, st_z, st_vx, st_vy, st_vz,
-                                      st_mass, factor_v, rho_B, *, mass_to_sun=1.0, mode="fast", device=0):
+                                      st_mass, factor_v, rho_B, *, mass_to_sun=None, mode=None, device=0):
     """Reference signature (halo_properties.py:282-286).  The gathers at :289-326 (DM inside
     Rmax, AMR gas -> particles through halo_gas.AMRgrid_to_particles, gas mass * rete**3) are
-    host-side numpy like the reference; everything from :333 on runs on the GPU."""
+    host-side numpy like the reference; everything from :333 on runs on the GPU.
+    mass_to_sun: masclet_framework.units.mass_to_sun (:293) when that package is importable, else it must be given."""
+    if mass_to_sun is None:
+        from . import gather
+        mass_to_sun = gather.default_mass_to_sun()
     dm_x, dm_y, dm_z = masclet_dm_data[0], masclet_dm_data[1], masclet_dm_data[2]
     dm_mass = masclet_dm_data[3] * mass_to_sun
     inside = np.sqrt((dm_x - cx) ** 2 + (dm_y - cy) ** 2 + (dm_z - cz) ** 2) < Rmax

@@ -39,6 +39,11 @@ class RunStats:
     passes: int
     pairs: int                        # (target, source) interactions: what the reference's loop visits
     evaluations: int = 0              # 1/r evaluations made for them (fewer than pairs in symmetric mode)
+    driver: int = 0                   # _lib.DRIVER_* that ran (fused: the whole loop was one kernel launch)
+    loop_ms: float = 0.0              # fused driver: duration of the persistent kernel by its own clock
+    comm_ms: float = 0.0              # split mode: CUDA-event time of the NCCL collectives
+    comm_bytes: int = 0               # split mode: bytes handed to the collectives
+    phase_ms: tuple = ()              # fused driver: prologue, potential, energy + compaction, tables, epilogue
 
 
 @dataclass
@@ -160,11 +165,12 @@ class UnbindPlan:
     HALMA_INCREMENTAL.
     """
 
-    def __init__(self, offsets, ext_offsets: Sequence = (), *, mode="fast", n_pre: int = 0,
+    def __init__(self, offsets, ext_offsets: Sequence = (), *, mode=None, n_pre: int = 0,
                  split_classes: bool = False, vb_fixed: bool = False, max_iter: int = 64,
                  G: float = G_CONST, kappa: float = 9.0, device: int = 0, rank: int = 0, n_ranks: int = 1,
                  use_graph: Optional[bool] = None, symmetric: Optional[bool] = None,
-                 cache_external: Optional[bool] = None, incremental: Optional[bool] = None):
+                 cache_external: Optional[bool] = None, incremental: Optional[bool] = None,
+                 driver: Optional[str] = None):
         L = _lib.lib()
         self._L = L
         self.offsets = _i64(offsets)
@@ -181,7 +187,7 @@ class UnbindPlan:
         cfg = _lib.UnbindConfig()
         cfg.struct_size = C.sizeof(_lib.UnbindConfig)
         cfg.device = device
-        cfg.mode = _lib.mode_code(mode)
+        cfg.mode = _lib.default_mode() if mode is None else _lib.mode_code(mode)      # None: HALMA_MODE
         cfg.n_groups = len(self.ext_offsets)
         cfg.n_pre = n_pre
         cfg.split_classes = int(bool(split_classes))
@@ -191,10 +197,15 @@ class UnbindPlan:
         cfg.kappa = float(kappa)
         cfg.rank = rank
         cfg.n_ranks = n_ranks
-        if use_graph is None:
+        # loop driver (halma_unbind_config.use_graph): "auto" = the persistent loop kernel on one GPU
+        # (one launch for the whole unbinding), "enqueue" = stand-alone kernels queued ahead by the host
+        # (per-launch events; always in split mode), "graph" = CUDA-graph WHILE node, "fused" = auto or fail
+        if driver is None:
             import os
-            use_graph = os.environ.get("HALMA_GRAPH", "0") not in ("0", "")
-        cfg.use_graph = int(bool(use_graph))
+            driver = "graph" if use_graph or (use_graph is None and os.environ.get("HALMA_GRAPH", "0") not in ("0", "")) \
+                else os.environ.get("HALMA_DRIVER", "auto")
+        cfg.use_graph = {"auto": _lib.DRIVER_AUTO, "graph": _lib.DRIVER_GRAPH, "enqueue": _lib.DRIVER_ENQUEUE,
+                         "fused": _lib.DRIVER_FUSED}[str(driver).lower()]
         if symmetric is None:
             import os
             symmetric = os.environ.get("HALMA_SYMMETRIC", "1") not in ("0", "")      # on unless HALMA_SYMMETRIC=0
@@ -291,7 +302,7 @@ class UnbindPlan:
         _lib.check(self._L.halma_plan_run(self._h, C.byref(st)))
         self._keep = []
         return RunStats(st.total_ms, st.potential_ms, st.potential_launches, st.launches, st.passes, st.pairs,
-                        st.evaluations)
+                        st.evaluations, st.driver, st.loop_ms, st.comm_ms, st.comm_bytes, tuple(st.phase_ms))
 
     def download_into(self, mask_addr=0, be_addr=0, energy_addr=0, idx_addr=0, halos_addr=0) -> None:
         """halma_plan_download into caller-owned host memory (raw addresses; 0 = skip): mask uint8[n],
@@ -351,7 +362,7 @@ def nccl_unique_id() -> bytes:
 
 def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (), n_pre: int = 0,
                      split_classes: bool = False, vb=None, kappa: float = 9.0, max_iter: int = 64,
-                     mode="fast", device: int = 0, G: float = G_CONST, temp=None,
+                     mode=None, device: int = 0, G: float = G_CONST, temp=None,
                      cold_T: float = 5 * 1e4, symmetric: Optional[bool] = None, streams: int = 1,
                      cache_external: Optional[bool] = None, incremental: Optional[bool] = None) -> CatalogueResult:
     """Unbind every halo of a catalogue in one batched, device-resident run.
@@ -460,7 +471,7 @@ def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, s
 
 def unbind_halo(x, y, z, vx, vy, vz, mass, *, pre: Sequence = (), post: Sequence = (),
                 split_classes: bool = False, kappa: float = 9.0, vb_fixed=None, max_iter: int = 64,
-                mode="fast", device: int = 0, G: float = G_CONST, symmetric: Optional[bool] = None,
+                mode=None, device: int = 0, G: float = G_CONST, symmetric: Optional[bool] = None,
                 cache_external: Optional[bool] = None, incremental: Optional[bool] = None) -> UnbindResult:
     """One halo.  pre / post: sequences of (mass, x, y, z) fixed source groups summed before /
     after the members (same keywords as oracle.unbind_halo)."""

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
-                          "--steps", "1", "--warmup", "1", "--ref-targets", "200"], capture_output=True, text=True,
+                          "--steps", "1", "--warmup", "1", "--ref-pairs", "4e6"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -27,3 +27,13 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_default_workload_is_the_catalogue():
+    """The default line of both arms is cfg3, the halo catalogue (BASELINE.json configs[2])."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--ref-pairs", "2e8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["config"]["workload"].startswith("cfg3") and d["scaling"] == "strong" and d["config"]["n_halo"] == 10000
+    assert d["value"] > 0 and "oracle calls" in d["cpu_baseline"]["sample"]

@@ -146,10 +146,25 @@ def test_stellar_unbinding_end_to_end_golden(snap, golden_dir):
     from test_oracle_gather import stellar_amr_inputs
     g = dict(np.load(os.path.join(golden_dir, "stellar_amr.npz")))
     a = stellar_amr_inputs(snap, g)
-    bound = halo_properties.escape_velocity_unbinding_fortran(*a, mode="exact")
+    bound = halo_properties.escape_velocity_unbinding_fortran(*a, mode="exact", mass_to_sun=1.0)
     np.testing.assert_array_equal(bound.astype(bool), g["bound"])
-    fast = halo_properties.escape_velocity_unbinding_fortran(*a, mode="fast").astype(bool)
+    fast = halo_properties.escape_velocity_unbinding_fortran(*a, mode="fast", mass_to_sun=1.0).astype(bool)
     assert np.count_nonzero(fast != g["bound"]) <= 2          # only energies within 1e-6 of zero may flip
+    # the DM masses are multiplied by masclet_framework.units.mass_to_sun (halo_properties.py:293): without that
+    # package the factor has to be given, and it must reach the DM masses (code units / 7 with factor 7 = the same)
+    with pytest.raises(ImportError):
+        halo_properties.escape_velocity_unbinding_fortran(*a, mode="exact")
+    a7 = list(a)
+    dm = a7[5]
+    a7[5] = (dm[0], dm[1], dm[2], np.asarray(dm[3]) / 7.0) + tuple(dm[4:])
+    b7 = halo_properties.escape_velocity_unbinding_fortran(*a7, mode="exact", mass_to_sun=7.0)
+    b1 = halo_properties.escape_velocity_unbinding_fortran(*a7, mode="exact", mass_to_sun=1.0)
+    assert np.count_nonzero(b7.astype(bool) != g["bound"]) <= 2 and np.count_nonzero(b1 != b7) > 0
+    # AMRgrid_to_particles (no particles) and st_gas_dm_particles_inside (with) alternate per halo in pyHALMA:
+    # the resident copy with particles serves both, nothing is uploaded twice
+    s_full = gather.snapshot_for(a[1], a[2], a[3], a[4], snap.masclet_dm_data, snap.masclet_st_data, 1.0, 0)
+    assert gather.snapshot_for(a[1], a[2], a[3], a[4], None, None, 1.0, 0) is s_full
+    assert gather.snapshot_for(a[1], a[2], a[3], a[4], snap.masclet_dm_data, snap.masclet_st_data, 1.0, 0) is s_full
     gather.release_cached_snapshot()
 
 

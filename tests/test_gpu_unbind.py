@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from pyhalma_b200 import halo_gas, halo_properties, synth
+from pyhalma_b200 import _lib, halo_gas, halo_properties, synth
 from pyhalma_b200.unbind import UnbindPlan, unbind_catalogue, unbind_halo
 
 pytestmark = pytest.mark.gpu
@@ -234,35 +234,48 @@ def test_idempotence_and_rerun():
 
 @pytest.mark.parametrize("mode", ["exact", "fast"])
 def test_graph_loop_driver_matches_enqueue_driver(mode):
-    # use_graph=1: the whole loop is one CUDA-graph launch with a device-side WHILE node
+    # The three loop drivers run the same phase code: "fused" (default on one GPU) is ONE persistent cooperative
+    # kernel for the whole loop, "enqueue" stand-alone kernels queued ahead by the host, "graph" one CUDA-graph
+    # launch with a device-side WHILE node.  Results must agree bit for bit.
     off, cols = ragged_catalogue()
     out = []
-    for use_graph in (False, True):
-        with UnbindPlan(off, mode=mode, kappa=1.0, use_graph=use_graph) as plan:
+    for driver in ("fused", "enqueue", "graph"):
+        with UnbindPlan(off, mode=mode, kappa=1.0, driver=driver) as plan:
             plan.upload_members(*cols)
             st = plan.run()
             res = plan.download()
-            st2 = plan.run()                     # re-launch of the instantiated graph
+            st2 = plan.run()                     # plans are re-runnable (re-launch of the instantiated graph)
             res2 = plan.download()
         assert np.array_equal(res.mask, res2.mask) and st.passes == st2.passes
+        assert np.array_equal(res.be32.view(np.uint32), res2.be32.view(np.uint32))
+        assert st.driver == {"fused": _lib.DRIVER_FUSED, "enqueue": _lib.DRIVER_ENQUEUE, "graph": _lib.DRIVER_GRAPH}[driver]
+        if driver == "fused":
+            # one launch per run (the first run of a plan on the predicate-free path also packs and sorts)
+            assert st2.launches == 1 and st2.potential_ms > 0 and st2.loop_ms >= st2.potential_ms
         out.append((st, res))
-    (sa, a), (sb, b) = out
-    assert sa.passes == sb.passes and sa.pairs == sb.pairs
-    assert np.array_equal(a.mask, b.mask) and np.array_equal(a.be32, b.be32) and np.array_equal(a.energy, b.energy)
-    assert np.array_equal(a.idx_packed, b.idx_packed)
-    assert [h.n_iter for h in a.halos] == [h.n_iter for h in b.halos]
-    # a large single halo through the predicate-free kernel inside the graph
+    (sa, a) = out[0]
+    for sb, b in out[1:]:
+        assert sa.passes == sb.passes and sa.pairs == sb.pairs and sa.evaluations == sb.evaluations
+        assert np.array_equal(a.mask, b.mask) and np.array_equal(a.be32.view(np.uint32), b.be32.view(np.uint32))
+        assert np.array_equal(a.energy, b.energy) and np.array_equal(a.idx_packed, b.idx_packed)
+        assert [h.n_iter for h in a.halos] == [h.n_iter for h in b.halos]
+        assert np.array_equal(a.halos.field("vb"), b.halos.field("vb")) and np.array_equal(a.halos.field("mass"), b.halos.field("mass"))
+    # a large single halo through the predicate-free kernel (+ symmetric self-term, cached and incremental sums)
     s, g, d = case(40000, 90000, 1000, extra=9)
     kw = dict(pre=[g.pos_mass()], post=[d.pos_mass()], kappa=9.0, mode=mode)
     if mode == "fast":
-        r0 = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, **kw)
         import os
-        os.environ["HALMA_GRAPH"] = "1"
-        try:
-            r1 = unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, **kw)
-        finally:
-            os.environ.pop("HALMA_GRAPH")
-        assert np.array_equal(r0.mask, r1.mask) and np.array_equal(r0.be32, r1.be32) and r0.n_iter == r1.n_iter
+        rs = []
+        for driver in ("fused", "enqueue", "graph"):
+            os.environ["HALMA_DRIVER"] = driver
+            try:
+                rs.append(unbind_halo(s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, **kw))
+            finally:
+                os.environ.pop("HALMA_DRIVER")
+        assert rs[0].stats.driver == _lib.DRIVER_FUSED and rs[1].stats.driver == _lib.DRIVER_ENQUEUE
+        for r1 in rs[1:]:
+            assert np.array_equal(rs[0].mask, r1.mask) and rs[0].n_iter == r1.n_iter
+            assert np.array_equal(rs[0].be32.view(np.uint32), r1.be32.view(np.uint32))
 
 
 def test_degenerate_inputs():
@@ -387,7 +400,7 @@ def test_stellar_onepass_golden(golden_dir):
         bound = halo_properties.escape_velocity_unbinding_fortran(
             rete, 40.0, 128, None, None, (dmx, dmy, dmz, dmm), cx, cy, cz, *g["vb"], 1.0, g["part_list"],
             glob["x"], glob["y"], glob["z"], glob["vx"], glob["vy"], glob["vz"], glob["mass"],
-            float(g["factor_v"]), 1.0, mode="exact")
+            float(g["factor_v"]), 1.0, mode="exact", mass_to_sun=1.0)
     finally:
         halo_gas.AMRgrid_to_particles = halo_gas_amr
     np.testing.assert_array_equal(bound, g["bound"])
