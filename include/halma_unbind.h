@@ -246,6 +246,10 @@ int halma_plan_use_comm(halma_plan *plan, halma_comm *comm);
  * repeatedly.  Blocks until done; stats may be null. */
 int halma_plan_run(halma_plan *plan, halma_run_stats *stats);
 
+/* Tuning aid: phase times (ns) of the first 16 passes of the last FUSED run: out48[3 * pass + k], k = potential,
+ * energy + compaction, commit + ticket table. */
+int halma_plan_debug_pass_ns(halma_plan *plan, uint32_t *out48);
+
 /* Any output pointer may be null.  mask/be/energy/idx are indexed like the member input
  * arrays: mask uint8[N]; be float32[N] (sum m/r at the last pass the particle took part
  * in); energy float64[N]; idx int32[N]: for halo h, idx[offsets[h] .. offsets[h]+n_bound)
@@ -253,9 +257,22 @@ int halma_plan_run(halma_plan *plan, halma_run_stats *stats);
 int halma_plan_download(halma_plan *plan, uint8_t *mask, float *be, double *energy, int32_t *idx,
                         halma_halo_result *halos);
 
-/* One-shot convenience for a single halo without externals bookkeeping on the caller's
- * side: create + upload + run + download + destroy.  groups_* are arrays of n_groups host
- * pointers / lengths. */
+/* One-shot catalogue call: create + upload + run + download + destroy.  HOST (or device) pointers.
+ * offsets: int64[n_halo + 1] CSR over the concatenated member arrays; group_offsets[g]: int64[n_halo + 1] CSR
+ * of external group g over its concatenated arrays group_mass[g], group_x[g], ...; vb: double[3 * n_halo]
+ * when cfg->vb_fixed, else may be null; temp (optional): member temperatures for the cold / hot mass sums
+ * (halo_gas.py:479-492).  Outputs as halma_plan_download; any may be null.  This is the batched form of
+ * the per-halo loop at pyHALMA.py:930-1067 for the unbinding step. */
+int halma_unbind_catalogue(const halma_unbind_config *cfg, int64_t n_halo, const int64_t *offsets,
+                           const double *x, const double *y, const double *z,
+                           const double *vx, const double *vy, const double *vz, const double *mass,
+                           const int64_t *const *group_offsets, const double *const *group_mass,
+                           const double *const *group_x, const double *const *group_y,
+                           const double *const *group_z, const double *vb, const double *temp, double cold_T,
+                           uint8_t *mask, float *be, double *energy, int32_t *idx,
+                           halma_halo_result *halos, halma_run_stats *stats);
+
+/* The same for a single halo: group_n[g] = length of group g's arrays. */
 int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n,
                       const double *x, const double *y, const double *z,
                       const double *vx, const double *vy, const double *vz, const double *mass,

@@ -24,7 +24,7 @@ EXPORTS = (
     "halma_host_alloc", "halma_host_free", "halma_potential_f32", "halma_potential_workspace_bytes",
     "halma_potential_f32_dev", "halma_plan_create", "halma_plan_destroy", "halma_plan_upload_members",
     "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join", "halma_comm_create", "halma_comm_destroy", "halma_plan_use_comm",
-    "halma_plan_run", "halma_plan_download", "halma_unbind_halo", "halma_microbench",
+    "halma_plan_run", "halma_plan_download", "halma_plan_debug_pass_ns", "halma_unbind_halo", "halma_unbind_catalogue", "halma_microbench",
     "halma_halo_shape_f32", "halma_sigma_projections_f32",
     "halma_snapshot_create", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_snapshot_upload_patch",
     "halma_snapshot_upload_particles", "halma_snapshot_gather", "halma_snapshot_gather_box", "halma_snapshot_fetch", "halma_last_kernel_ms",
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
     L.halma_plan_use_comm.argtypes = [vp, vp]
     L.halma_plan_run.argtypes = [vp, C.POINTER(RunStats)]
     L.halma_plan_download.argtypes = [vp, vp, vp, vp, vp, C.POINTER(HaloResult)]
+    L.halma_plan_debug_pass_ns.argtypes = [vp, vp]
     L.halma_microbench.argtypes = [i32, f64p]
     L.halma_halo_shape_f32.argtypes = [i32, vp, vp, vp, vp, i64, vp]
     L.halma_sigma_projections_f32.argtypes = ([i32, i64, vp, C.c_int32, vp, i64] + [vp] * 7 + [C.c_float] * 7 + [vp])

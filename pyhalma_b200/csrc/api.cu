@@ -474,6 +474,8 @@ struct halma_plan {
     std::vector<std::vector<int64_t>> ext_offsets;
     std::vector<int> group_seg;           // segment index of each ext group inside HaloDesc::seg
     std::vector<int> group_max;           // largest per-halo count of each group
+    std::vector<HaloDesc> host_halo;      // host copies of the static tables (sources of asynchronous uploads)
+    std::vector<int32_t> host_order, host_rank_of, host_chunk_halo, host_chunk_p0;
     bool members_up = false, vb_up = false;
     std::vector<bool> group_up;
 
@@ -606,9 +608,14 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     const int members_slot = cfg.n_pre;
     for (int g = 0; g < cfg.n_groups; ++g) P->group_seg[g] = g < cfg.n_pre ? g : g + 1;
 
-    std::vector<HaloDesc> halo(nh);
-    std::vector<int32_t> chunk_halo, chunk_p0;
+    // host tables live in the plan: their asynchronous uploads need no synchronisation here
+    std::vector<HaloDesc> &halo = P->host_halo;
+    halo.assign(nh, HaloDesc());
+    std::vector<int32_t> &chunk_halo = P->host_chunk_halo, &chunk_p0 = P->host_chunk_p0;
+    chunk_halo.clear();
+    chunk_p0.clear();
     int64_t poff = 0, eoff = 0, soff = 0, doff = 0;
+    const int chunk = P->n_user <= kChunkSmallMaxMembers ? kChunkSmall : kChunk;
     {
         const char *e = getenv("HALMA_NP");
         P->np = cfg.mode == HALMA_MODE_FAST && !(e && atoi(e) == 0);
@@ -622,7 +629,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
         d.n0 = static_cast<int32_t>(n0);
         d.nseg = 1 + cfg.n_groups;
         d.chunk_begin = static_cast<int32_t>(chunk_halo.size());
-        for (int64_t q = 0; q < n0; q += kChunk) {
+        for (int64_t q = 0; q < n0; q += chunk) {
             chunk_halo.push_back(static_cast<int32_t>(h));
             chunk_p0.push_back(static_cast<int32_t>(q));
         }
@@ -666,7 +673,8 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
         if (pairs < min_pairs) P->np = false;
     }
 
-    std::vector<int32_t> order(nh);
+    std::vector<int32_t> &order = P->host_order;
+    order.assign(nh, 0);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return halo[a].n0 > halo[b].n0; });
 
@@ -678,7 +686,8 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(P->d_rank_of.alloc(nh));
     CU_TRY(P->d_sched.alloc(nh));
     CU_TRY(P->d_range.alloc(6 * nh));
-    std::vector<int32_t> rank_of(nh);
+    std::vector<int32_t> &rank_of = P->host_rank_of;
+    rank_of.assign(nh, 0);
     for (int64_t k = 0; k < nh; ++k) rank_of[order[k]] = static_cast<int32_t>(k);
     if (nh) {
         CU_TRY(cudaMemcpyAsync(P->d_rank_of.p, rank_of.data(), nh * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -696,7 +705,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
         CU_TRY(cudaMemcpyAsync(P->d_ext_off[g].p, P->ext_offsets[g].data(), (nh + 1) * 8, cudaMemcpyHostToDevice, s));
         stage = std::max<int64_t>(stage, P->ext_offsets[g][nh]);
     }
-    CU_TRY(cudaStreamSynchronize(s));      // host vectors go out of scope
+    // the host tables stay alive in the plan until the copies have certainly been made (first run)
 
     const size_t NU = static_cast<size_t>(P->n_user), NP = static_cast<size_t>(P->n_pad);
     CU_TRY(P->d_in.alloc(7 * NU));
@@ -760,7 +769,8 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(cudaMemsetAsync(P->d_work.p, 0, 8 * NP * sizeof(float), s));
     CU_TRY(cudaMemsetAsync(P->d_ext.p, 0, 4 * static_cast<size_t>(P->n_ext_pad) * sizeof(float), s));
     CU_TRY(cudaMemsetAsync(P->d_vb_user.p, 0, 3 * nh * sizeof(double), s));
-    CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&P->h_flags), sizeof(int32_t) * (cfg.max_iter + 1)));
+    // (the pinned convergence flags of the enqueue-ahead driver are allocated on first use: cudaMallocHost and
+    // cudaFreeHost synchronise the device, which would serialise plans that run side by side)
     // events of the multi-launch drivers are created on first use (plan_run)
     CU_TRY(cudaEventCreate(&P->ev_start));
     CU_TRY(cudaEventCreate(&P->ev_stop));
@@ -774,6 +784,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.order = P->d_order.p;
     L.n_halo = static_cast<int32_t>(nh);
     L.n_chunks = P->n_chunks;
+    L.chunk = P->n_user <= kChunkSmallMaxMembers ? kChunkSmall : kChunk;
     L.n_pad = P->n_pad;
     L.n_user = P->n_user;
     const double *in = P->d_in.p;
@@ -945,7 +956,6 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     P->fused_index = cfg.n_ranks == 1 ? fused_kernel_index(cfg.mode, P->variant, P->np, P->sym) : -1;
     if (cfg.use_graph == HALMA_DRIVER_FUSED && P->fused_index < 0)
         return fail(HALMA_ERR_INVALID, "no persistent loop kernel for this plan (split mode or a tuning kernel shape)");
-    CU_TRY(cudaStreamSynchronize(s));
     return HALMA_OK;
 }
 
@@ -1317,6 +1327,8 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
     memset(&hst, 0, sizeof hst);
 
     if (driver != HALMA_DRIVER_FUSED && P->ev.empty()) {
+        if (!P->h_flags)
+            CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&P->h_flags), sizeof(int32_t) * (P->cfg.max_iter + 1)));
         P->ev.resize(3 * static_cast<size_t>(P->cfg.max_iter));
         for (auto &e : P->ev) CU_TRY(cudaEventCreate(&e));
         if (P->cfg.n_ranks > 1) {
@@ -1433,7 +1445,10 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         stats->launches = launches;
         stats->passes = passes;
         stats->driver = driver;
-        if (nh) {
+        if (nh && driver == HALMA_DRIVER_FUSED) {
+            stats->pairs = static_cast<int64_t>(hst.pairs_total);
+            stats->evaluations = static_cast<int64_t>(hst.evals_total);
+        } else if (nh) {
             std::vector<unsigned long long> pr(nh);
             CU_TRY(cudaMemcpy(pr.data(), P->d_pairs.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             unsigned long long t = 0;
@@ -1445,6 +1460,17 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
             stats->evaluations = static_cast<int64_t>(t);
         }
     }
+    return HALMA_OK;
+}
+
+// Tuning aid: per-pass phase times of the last FUSED run (potential, energy + compaction, tables; ns), first 16 passes.
+extern "C" int halma_plan_debug_pass_ns(halma_plan *P, uint32_t *out48)
+{
+    if (!P || !out48) return fail(HALMA_ERR_INVALID, "null pointer");
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    LoopState hst;
+    CU_TRY(cudaMemcpy(&hst, P->d_st.p, sizeof hst, cudaMemcpyDeviceToHost));
+    memcpy(out48, hst.pass_ns, sizeof hst.pass_ns);
     return HALMA_OK;
 }
 
@@ -1497,6 +1523,32 @@ extern "C" int halma_plan_download(halma_plan *P, uint8_t *mask, float *be, doub
     return HALMA_OK;
 }
 
+extern "C" int halma_unbind_catalogue(const halma_unbind_config *cfg, int64_t n_halo, const int64_t *offsets,
+                                      const double *x, const double *y, const double *z, const double *vx,
+                                      const double *vy, const double *vz, const double *mass,
+                                      const int64_t *const *group_offsets, const double *const *group_mass,
+                                      const double *const *group_x, const double *const *group_y,
+                                      const double *const *group_z, const double *vb, const double *temp,
+                                      double cold_T, uint8_t *mask, float *be, double *energy, int32_t *idx,
+                                      halma_halo_result *halos, halma_run_stats *stats)
+{
+    if (!cfg) return fail(HALMA_ERR_INVALID, "null config");
+    if (cfg->n_groups > 0 && (!group_offsets || !group_mass || !group_x || !group_y || !group_z))
+        return fail(HALMA_ERR_INVALID, "null group table");
+    halma_plan *P = nullptr;
+    int rc = halma_plan_create(cfg, n_halo, offsets, group_offsets, &P);
+    if (rc) return rc;
+    rc = halma_plan_upload_members(P, x, y, z, vx, vy, vz, mass);
+    for (int g = 0; !rc && g < cfg->n_groups; ++g)
+        rc = halma_plan_upload_group(P, g, group_mass[g], group_x[g], group_y[g], group_z[g]);
+    if (!rc && cfg->vb_fixed) rc = vb ? halma_plan_set_vb(P, vb) : fail(HALMA_ERR_INVALID, "vb_fixed = 1 needs vb");
+    if (!rc && temp) rc = halma_plan_upload_temp(P, temp, cold_T);
+    if (!rc) rc = halma_plan_run(P, stats);
+    if (!rc) rc = halma_plan_download(P, mask, be, energy, idx, halos);
+    halma_plan_destroy(P);
+    return rc;
+}
+
 extern "C" int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n, const double *x, const double *y,
                                  const double *z, const double *vx, const double *vy, const double *vz,
                                  const double *mass, const int64_t *group_n, const double *const *group_mass,
@@ -1506,27 +1558,18 @@ extern "C" int halma_unbind_halo(const halma_unbind_config *cfg, int64_t n, cons
 {
     if (!cfg) return fail(HALMA_ERR_INVALID, "null config");
     if (n < 0) return fail(HALMA_ERR_INVALID, "negative size");
-    if (cfg->n_groups > 0 && (!group_n || !group_mass || !group_x || !group_y || !group_z))
-        return fail(HALMA_ERR_INVALID, "null group table");
+    if (cfg->n_groups > 0 && !group_n) return fail(HALMA_ERR_INVALID, "null group table");
+    if (cfg->n_groups < 0 || cfg->n_groups > HALMA_MAX_GROUPS) return fail(HALMA_ERR_INVALID, "bad n_groups");
     const int64_t offsets[2] = {0, n};
     int64_t eo[HALMA_MAX_GROUPS][2];
     const int64_t *eop[HALMA_MAX_GROUPS];
-    for (int g = 0; g < cfg->n_groups && g < HALMA_MAX_GROUPS; ++g) {
+    for (int g = 0; g < cfg->n_groups; ++g) {
         eo[g][0] = 0;
         eo[g][1] = group_n[g];
         eop[g] = eo[g];
     }
-    halma_plan *P = nullptr;
-    int rc = halma_plan_create(cfg, 1, offsets, eop, &P);
-    if (rc) return rc;
-    rc = halma_plan_upload_members(P, x, y, z, vx, vy, vz, mass);
-    for (int g = 0; !rc && g < cfg->n_groups; ++g)
-        rc = halma_plan_upload_group(P, g, group_mass[g], group_x[g], group_y[g], group_z[g]);
-    if (!rc && cfg->vb_fixed) rc = vb ? halma_plan_set_vb(P, vb) : fail(HALMA_ERR_INVALID, "vb_fixed = 1 needs vb");
-    if (!rc) rc = halma_plan_run(P, stats);
-    if (!rc) rc = halma_plan_download(P, mask, be, energy, idx, result);
-    halma_plan_destroy(P);
-    return rc;
+    return halma_unbind_catalogue(cfg, 1, offsets, x, y, z, vx, vy, vz, mass, eop, group_mass, group_x, group_y, group_z,
+                                  vb, nullptr, 0.0, mask, be, energy, idx, result, stats);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1603,18 +1646,30 @@ static int potential_via_plan(int device, const float *sm, const float *sx, cons
 {
     const size_t tb = static_cast<size_t>(n_tgt) * sizeof(float);
     const int64_t off = find_target_block(sx, sy, sz, n_src, tx, ty, tz, n_tgt);
-    if (off < 0) return kPlanPathDeclined;
-    // external groups: the sources before and after the block
+    // cross call (DM -> gas, stars -> gas, gas -> stars ...): the targets become massless members that are not
+    // sources, all sources one external group; predicate-free kernel + correction tickets, no symmetric term.
+    // A target that coincides with a source (subsampled self calls) sends the call to the predicated kernel
+    // through the usual fallback, so the result is always the reference's.
+    const bool cross = off < 0;
+    const char *ce = getenv("HALMA_POT_PLAN_CROSS");
+    if (cross && ce && atoi(ce) == 0) return kPlanPathDeclined;
+    // external groups: the sources before and after the block (all of them for a cross call)
     int64_t g_begin[2], g_count[2];
     int n_groups = 0, n_pre = 0;
-    if (off > 0) {
-        g_begin[n_groups] = 0;
-        g_count[n_groups++] = off;
-        n_pre = 1;
-    }
-    if (off + n_tgt < n_src) {
-        g_begin[n_groups] = off + n_tgt;
-        g_count[n_groups++] = n_src - off - n_tgt;
+    if (cross) {
+        g_begin[0] = 0;
+        g_count[0] = n_src;
+        n_groups = n_pre = 1;
+    } else {
+        if (off > 0) {
+            g_begin[n_groups] = 0;
+            g_count[n_groups++] = off;
+            n_pre = 1;
+        }
+        if (off + n_tgt < n_src) {
+            g_begin[n_groups] = off + n_tgt;
+            g_count[n_groups++] = n_src - off - n_tgt;
+        }
     }
     halma_unbind_config cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -1628,7 +1683,10 @@ static int potential_via_plan(int device, const float *sm, const float *sx, cons
     cfg.G = 1.0;
     cfg.kappa = 1.0;
     cfg.n_ranks = 1;
-    cfg.symmetric = 1;
+    {
+        const char *e = getenv("HALMA_SYMMETRIC");      // the same switch as the plans of the Python layer
+        cfg.symmetric = (!cross && !(e && atoi(e) == 0)) ? 1 : 0;
+    }
     const int64_t offsets[2] = {0, n_tgt};
     const int64_t eo[2][2] = {{0, n_groups > 0 ? g_count[0] : 0}, {0, n_groups > 1 ? g_count[1] : 0}};
     const int64_t *eop[2] = {eo[0], eo[1]};
@@ -1641,18 +1699,22 @@ static int potential_via_plan(int device, const float *sm, const float *sx, cons
         ~Guard() { halma_plan_destroy(p); }
     } guard{P};
     if (!P->np) return kPlanPathDeclined;          // e.g. too many particles for the sorted copies
+    if (cross) {
+        P->lp.targets_only = 1;
+        P->pp.targets_only = 1;
+    }
     cudaStream_t s = P->stream;
     g_alloc_stream = s;
     {
-        // targets -> the plan's float64 member arrays (exact), velocities zero, masses of the block
+        // targets -> the plan's float64 member arrays (exact), velocities zero, masses of the block (cross: zero)
         DBuf<float> stage;
         CU_TRY(stage.alloc(4 * static_cast<size_t>(n_tgt)));
-        const float *h[4] = {tx, ty, tz, sm + off};
+        const float *h[4] = {tx, ty, tz, cross ? nullptr : sm + off};
         for (int k = 0; k < 4; ++k)
             if (h[k]) CU_TRY(cudaMemcpyAsync(stage.p + k * n_tgt, h[k], tb, cudaMemcpyHostToDevice, s));
         const int grid = static_cast<int>(std::min<int64_t>((n_tgt + 255) / 256, P->ctx->sm_count * 8));
         k_widen_members<<<grid, 256, 0, s>>>(stage.p, stage.p + n_tgt, stage.p + 2 * n_tgt,
-                                             stage.p + 3 * n_tgt, n_tgt, P->d_in.p);
+                                             cross ? nullptr : stage.p + 3 * n_tgt, n_tgt, P->d_in.p);
         CU_TRY(cudaGetLastError());
         P->members_up = true;
         P->sorted_dirty = true;

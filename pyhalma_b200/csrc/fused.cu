@@ -47,18 +47,20 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const Pot
                                                                         const int do_pack)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ LoopSmem sm;
     static_assert(kLT == kPotentialBlock, "the loop phases run on the potential kernel's blocks");
+    static_assert(kSchedSmemBytes <= kWarpsPerBlock * kStages * kStageFloats * 4, "the ticket table is built in the ring buffers");
     cg::grid_group grid = cg::this_grid();
     LoopState *st = lp.st;
     const bool clock = blockIdx.x == 0 && threadIdx.x == 0;
     const unsigned long long t_begin = clock ? globaltimer_ns() : 0ull;
     unsigned long long t_ph[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
     unsigned long long t_last = t_begin;
+    int pass = 0, par = 0;
     auto lap = [&](int k) {          // block 0's clock; the barriers make its phase times the grid's
         if (clock) {
             const unsigned long long t = globaltimer_ns();
             t_ph[k] += t - t_last;
+            if (k >= 1 && k <= 3 && pass < 16) st->pass_ns[pass][k - 1] = static_cast<unsigned int>(t - t_last);
             t_last = t;
         }
     };
@@ -78,20 +80,19 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const Pot
         }
     }
     if (do_pack) {
-        for (int c = blockIdx.x; c < lp.n_chunks; c += gridDim.x) pack_chunk(lp, sm, c);
+        pack_phase(lp);
         fence_proxy_async_global();
         grid.sync();
     }
-    for (int h = blockIdx.x; h < lp.n_halo; h += gridDim.x) decide_halo(lp, sm, h, 1, 0, 0);
+    decide_init_phase(lp);
     fence_proxy_async_global();
     grid.sync();
     commit_phase(lp, 1);
-    if (blockIdx.x == 0) schedule_block(lp, sm, 1);
+    if (blockIdx.x == 0) schedule_block(lp, smem_raw, 1);      // the TMA ring is idle between passes
     grid.sync();
     lap(0);
 
     // ---- passes ----
-    int pass = 0, par = 0;
     while (*reinterpret_cast<volatile int32_t *>(&st->any_active)) {
         if constexpr (T == 0)
             potential_pass_exact(pp, rg);
@@ -107,13 +108,13 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const Pot
             }
         }
         lap(1);
-        energy_phase(lp, sm, par, pass);
-        compact_phase(lp, sm, par, pass, true);
+        energy_phase(lp, par, pass);
+        compact_phase(lp, par, pass, true);
         fence_proxy_async_global();
         grid.sync();
         lap(2);
         commit_phase(lp, 0);
-        if (blockIdx.x == 0) schedule_block(lp, sm, 0);
+        if (blockIdx.x == 0) schedule_block(lp, smem_raw, 0);
         grid.sync();
         lap(3);
         ++pass;
@@ -122,6 +123,22 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const Pot
 
     // ---- epilogue ----
     finalize_phase(lp);
+    {
+        // run totals of the per-halo counters (exact integer atomics)
+        unsigned long long pr = 0ull, ev = 0ull;
+        for (int h = blockIdx.x * kLT + threadIdx.x; h < lp.n_halo; h += gridDim.x * kLT) {
+            pr += lp.pairs[h];
+            ev += lp.evals[h];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            pr += __shfl_down_sync(0xffffffffu, pr, o);
+            ev += __shfl_down_sync(0xffffffffu, ev, o);
+        }
+        if ((threadIdx.x & 31) == 0 && (pr | ev)) {
+            atomicAdd(&st->pairs_total, pr);
+            atomicAdd(&st->evals_total, ev);
+        }
+    }
     lap(4);
     if (clock) {
         st->pot_ns = t_ph[1];

@@ -16,11 +16,7 @@
 
 namespace halma {
 
-__global__ void __launch_bounds__(kLT) k_pack_members(const LoopParams p)
-{
-    __shared__ LoopSmem sm;
-    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) pack_chunk(p, sm, c);
-}
+__global__ void __launch_bounds__(kLT) k_pack_members(const LoopParams p) { pack_phase(p); }
 
 // ---------------------------------------------------------------------------------------
 // One external group: user CSR layout (float64) -> padded float32 segment of each halo.
@@ -44,36 +40,30 @@ __global__ void __launch_bounds__(256) k_pack_group(const HaloDesc *halo, int n_
 
 __global__ void __launch_bounds__(kLT) k_energy_flag(const LoopParams p)
 {
-    __shared__ LoopSmem sm;
     if (!p.st->any_active) return;
-    energy_phase(p, sm, p.st->parity, p.st->pass);
+    energy_phase(p, p.st->parity, p.st->pass);
 }
 
-// init = 1 right after k_pack_members (no pass made yet); passes decide inside k_energy_flag.
-__global__ void __launch_bounds__(kLT) k_halo_decide_init(const LoopParams p)
-{
-    __shared__ LoopSmem sm;
-    for (int h = blockIdx.x; h < p.n_halo; h += gridDim.x) decide_halo(p, sm, h, 1, 0, 0);
-}
+// Right after k_pack_members (no pass made yet); the passes decide inside k_energy_flag.
+__global__ void __launch_bounds__(kLT) k_halo_decide_init(const LoopParams p) { decide_init_phase(p); }
 
 __global__ void __launch_bounds__(kLT) k_compact(const LoopParams p)
 {
-    __shared__ LoopSmem sm;
     if (!p.st->any_active) return;
-    compact_phase(p, sm, p.st->parity, p.st->pass, false);
+    compact_phase(p, p.st->parity, p.st->pass, false);
 }
 
 // Every block commits its share of the haloes; block 0 also builds the ticket table.
 __global__ void __launch_bounds__(kLT) k_schedule(const LoopParams p, int init)
 {
-    __shared__ LoopSmem sm;
+    __shared__ __align__(16) unsigned char smem[kSchedSmemBytes];
     if (!init && !p.st->any_active) {
         // graph driver: nothing left to do, leave the WHILE node
         if (blockIdx.x == 0 && threadIdx.x == 0 && p.cond_handle) cudaGraphSetConditional(p.cond_handle, 0u);
         return;
     }
     commit_phase(p, init);
-    if (blockIdx.x == 0) schedule_block(p, sm, init);
+    if (blockIdx.x == 0) schedule_block(p, smem, init);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -88,7 +78,7 @@ __global__ void __launch_bounds__(256) k_fold_partials(const LoopParams p)
         if (!p.active[h]) continue;
         const int n = p.cnt[h];
         const int q = p.chunk_p0[c] + threadIdx.x;
-        if (q >= n) continue;
+        if (q >= n || threadIdx.x >= p.chunk) continue;      // (a block covers the largest chunk size)
         const int64_t i = p.halo[h].poff + q;
         const int owner = (q / p.group_size) % p.n_ranks;
         double phi = 0.0;
@@ -136,10 +126,11 @@ __global__ void __launch_bounds__(kLT) k_finalize(const LoopParams p) { finalize
 // ---------------------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------------------
+// one warp per chunk, grid-stride
 static inline int chunk_grid(const LoopParams &p, int sm_count)
 {
-    const int want = sm_count * 8;
-    return p.n_chunks < want ? (p.n_chunks > 0 ? p.n_chunks : 1) : want;
+    const int want = sm_count * 16, need = (p.n_chunks + kLW - 1) / kLW;
+    return need < want ? (need > 0 ? need : 1) : want;
 }
 
 cudaError_t launch_pack_members(const LoopParams &p, int sm_count, cudaStream_t s)
@@ -168,8 +159,8 @@ cudaError_t launch_energy_flag(const LoopParams &p, int sm_count, cudaStream_t s
 
 cudaError_t launch_halo_decide_init(const LoopParams &p, int sm_count, cudaStream_t s)
 {
-    const int want = sm_count * 8;
-    const int g = p.n_halo < want ? (p.n_halo > 0 ? p.n_halo : 1) : want;
+    const int want = sm_count * 16, need = (p.n_halo + kLW - 1) / kLW;
+    const int g = need < want ? (need > 0 ? need : 1) : want;
     k_halo_decide_init<<<g, kLT, 0, s>>>(p);
     return cudaGetLastError();
 }

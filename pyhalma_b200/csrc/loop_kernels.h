@@ -7,7 +7,9 @@
 
 namespace halma {
 
-constexpr int kChunk = 256;               // members per bookkeeping chunk
+constexpr int kChunk = 256;               // members per bookkeeping chunk (one warp each) ...
+constexpr int kChunkSmall = 64;           // ... and in plans with few members, where latency counts, not bandwidth
+constexpr int kChunkSmallMaxMembers = 1 << 18;
 constexpr int kChunkSums = 10;            // float64 sums kept per chunk
 constexpr int kMinSplitSources = 2048;    // never split a halo's sources into pieces below this
 constexpr int kMaxSplit = 8;              // planes of the partial-potential buffer
@@ -18,6 +20,7 @@ struct LoopParams {
     const HaloDesc *halo;
     const int32_t *chunk_halo, *chunk_p0, *order;
     int32_t n_halo, n_chunks;
+    int32_t chunk;                        // members per chunk: kChunk or kChunkSmall
     int64_t n_pad, n_user;
     // pristine float64 members in the user's layout
     const double *x64, *y64, *z64, *vx, *vy, *vz, *m64;
@@ -79,6 +82,7 @@ struct LoopParams {
     int32_t *rem_cnt;                     // [n_halo]
     int32_t *incr;                        // [n_halo] the coming / current pass of the halo is incremental
     int32_t incr_enabled;
+    int32_t targets_only;                 // members are targets only (the f2py-level cross call): counters follow
     // CUDA-graph loop driver: conditional handle of the WHILE node (0 = not in a graph)
     unsigned long long cond_handle;
 };

@@ -650,7 +650,11 @@ __device__ __forceinline__ void potential_pass_fast(const PotParams &p, Ring &rg
         // pass (externals and corrections included) and no correction ticket is needed.
         const bool incr = REUSE && p.incr_enabled && p.incr[tk.h];
         int filt = 0, nphase = 1;
-        if (REUSE && p.cache_ext && hd->n_ext > 0 && !incr) {
+        if (p.targets_only) {
+            // the f2py-level call with targets that are not sources (api.cu::potential_via_plan): the members
+            // carry no mass, only the external segments are summed
+            filt = 2;
+        } else if (REUSE && p.cache_ext && hd->n_ext > 0 && !incr) {
             if (st->pass == 0) {
                 filt = 1;
                 nphase = 2;

@@ -304,6 +304,13 @@ class UnbindPlan:
         return RunStats(st.total_ms, st.potential_ms, st.potential_launches, st.launches, st.passes, st.pairs,
                         st.evaluations, st.driver, st.loop_ms, st.comm_ms, st.comm_bytes, tuple(st.phase_ms))
 
+    def debug_pass_us(self):
+        """Tuning aid: (potential, energy + compaction, tables) in microseconds for the first 16 passes of the
+        last run with the persistent loop kernel."""
+        out = (C.c_uint32 * 48)()
+        _lib.check(self._L.halma_plan_debug_pass_ns(self._h, out))
+        return [tuple(out[3 * k + j] / 1e3 for j in range(3)) for k in range(16)]
+
     def download_into(self, mask_addr=0, be_addr=0, energy_addr=0, idx_addr=0, halos_addr=0) -> None:
         """halma_plan_download into caller-owned host memory (raw addresses; 0 = skip): mask uint8[n],
         be float32[n], energy float64[n], idx int32[n], halos halma_halo_result[n_halo]."""

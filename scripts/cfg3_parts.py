@@ -29,8 +29,9 @@ def run_part(cat, costs, world, rank, steps, graph):
         st = plan.run()
         tot += st.total_ms
         pot += st.potential_ms
+    per_pass = plan.debug_pass_us()[:st.passes]
     plan.close()
-    return dict(world=world, rank=rank, n_halo=len(parts[rank]), n=int(off[-1]), ms=tot / steps, pot_ms=pot / steps,
+    return dict(per_pass_us=[[round(v, 1) for v in t] for t in per_pass], world=world, rank=rank, n_halo=len(parts[rank]), n=int(off[-1]), ms=tot / steps, pot_ms=pot / steps,
                 passes=st.passes, launches=st.launches, pairs=st.pairs, evals=st.evaluations,
                 phase_ms=[round(v, 4) for v in st.phase_ms], loop_ms=st.loop_ms)
 

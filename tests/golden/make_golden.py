@@ -36,19 +36,28 @@ from oracle import oracle as O  # noqa: E402
 from pyhalma_b200 import synth  # noqa: E402
 
 CALLS = []
+CALL_INPUTS = []          # filled only while RECORD_INPUTS is on (call_sequences())
+RECORD_INPUTS = False
+
+
+def _record(ntotal, ntest, out, args):
+    CALLS.append((int(ntotal), int(ntest), out.copy()))
+    if RECORD_INPUTS:
+        # exactly what reached the f2py boundary: dtypes as the reference's wrapper made them (halo_gas.py:172-178)
+        CALL_INPUTS.append([np.array(a) for a in args])
 
 
 class _RecordingParticle:
     @staticmethod
     def brute_force_binding_energy(ncores, ntotal, tm, tx, ty, tz, ntest, sx, sy, sz):
         out = O.brute_force_binding_energy(ncores, ntotal, tm, tx, ty, tz, ntest, sx, sy, sz)
-        CALLS.append((int(ntotal), int(ntest), out.copy()))
+        _record(ntotal, ntest, out, (tm, tx, ty, tz, sx, sy, sz))
         return out
 
     @staticmethod
     def serial_brute_force_binding_energy(ntotal, tm, tx, ty, tz, ntest, sx, sy, sz):
         out = O.serial_brute_force_binding_energy(ntotal, tm, tx, ty, tz, ntest, sx, sy, sz)
-        CALLS.append((int(ntotal), int(ntest), out.copy()))
+        _record(ntotal, ntest, out, (tm, tx, ty, tz, sx, sy, sz))
         return out
 
     @staticmethod
@@ -289,8 +298,61 @@ def stellar_amr():
     print("stellar_amr members", len(part_list), "bound", int(np.sum(bound)), "sources", int(d["call0_ntotal"]))
 
 
+def call_sequences():
+    """The kernel-call SEQUENCES of the reference's drivers with their inputs: every call that
+    halo_gas.RPS, halo_gas.most_bound_particle and halo_properties.escape_velocity_unbinding_fortran make
+    through `particle.particle.brute_force_binding_energy` on the small cases above, in order, with the
+    float32 arrays that crossed the f2py boundary and the result the (oracle-backed) module returned.
+    tests/test_gpu_unbind.py replays them through the drop-in package in EXACT mode, bit for bit.
+    Runs the same cases as main() again (same seeds) and checks the outputs against the fixtures
+    main() wrote, so the two files cannot drift apart."""
+    global RECORD_INPUTS
+    from python_scripts import halo_gas
+    RECORD_INPUTS = True
+    d = {}
+    mass_dm_part = 8e7
+    try:
+        for tag, two_species, lim, seed in (("rps_one_dm", False, 5000, 11), ("rps_two_dm", True, 5000, 12),
+                                            ("rps_sampled", True, 100, 13)):
+            g = dict(np.load(os.path.join(HERE, tag + ".npz")))
+            stars, gas, dm = small_case(seed, two_species)
+            vb = g["vb"]
+            for part, run in (("rps", lambda: halo_gas.RPS(
+                    gas.x, gas.y, gas.z, gas.vx, gas.vy, gas.vz, gas.mass, gas.temp, dm.x, dm.y, dm.z, dm.mass,
+                    stars.x, stars.y, stars.z, stars.mass, vb[0], vb[1], vb[2], lim, mass_dm_part,
+                    2 if two_species else 1)),
+                              ("mb", lambda: halo_gas.most_bound_particle(
+                                  gas.x, gas.y, gas.z, gas.mass, dm.x, dm.y, dm.z, dm.mass, stars.x, stars.y, stars.z,
+                                  stars.mass, np.arange(len(stars)) + 1000, lim, mass_dm_part))):
+                CALLS.clear()
+                CALL_INPUTS.clear()
+                np.random.seed(4242)
+                run()
+                pre = "" if part == "rps" else "mb_"
+                assert len(CALLS) == int(g[pre + "n_calls"]), (tag, part)
+                d["%s_%s_n_calls" % (tag, part)] = np.int64(len(CALLS))
+                for k, ((nt, ns, out), ins) in enumerate(zip(CALLS, CALL_INPUTS)):
+                    assert np.array_equal(out.view(np.uint32), g["%scall%d_be" % (pre, k)].view(np.uint32)), (tag, part, k)
+                    for name, a in zip(("tm", "tx", "ty", "tz", "sx", "sy", "sz"), ins):
+                        assert a.dtype == np.float32, (tag, part, k, name, a.dtype)
+                        d["%s_%s_call%d_%s" % (tag, part, k, name)] = a
+                    d["%s_%s_call%d_be" % (tag, part, k)] = out
+    finally:
+        RECORD_INPUTS = False
+        CALLS.clear()
+        CALL_INPUTS.clear()
+    np.savez_compressed(os.path.join(HERE, "call_sequences.npz"), **d)
+    print("call_sequences:", {k: int(v) for k, v in d.items() if k.endswith("n_calls")})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "calls":
+        # only the call sequences, checked against the existing fixtures (which stay as they are)
+        install_stubs()
+        call_sequences()
+        sys.exit(0)
     main()
     shape_and_sigma()
     gather_amr()
     stellar_amr()
+    call_sequences()

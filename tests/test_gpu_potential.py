@@ -208,7 +208,8 @@ def test_large_calls_through_a_plan(monkeypatch):
     """Large FAST calls of halma_potential_f32 whose targets are a block of the sources run as a one-pass plan
     (from HALMA_POT_PLAN_MIN_PAIRS pairs on, default 1e10): predicate-free kernel + correction tickets + symmetric
     self-term.  Every shape the reference's callers have, against the direct (predicated) path and the float64
-    oracle; calls whose targets are other particles stay on the direct path."""
+    oracle.  Calls whose targets are other particles (DM -> gas, stars -> gas) run as a plan too, with the targets
+    as massless members that are not sources; targets that coincide with sources then go through the fallback."""
     rng = np.random.default_rng(77)
     st = synth.plummer_stars(50_000, 6 * synth.KPC, 1e6, rng)
     synth.add_coincident_pairs(st, 5, rng)                      # shared coordinates -> correction tickets
@@ -225,8 +226,9 @@ def test_large_calls_through_a_plan(monkeypatch):
         # block at the very start / end of the sources
         "block first": (all_src, gas),
         "block last": (all_src, dm),
-        # targets are other particles (stars -> gas): direct path
+        # targets are other particles (stars -> gas; lattice gas -> stars, whole planes of sources share a coordinate)
         "cross": ([st.mass, st.x, st.y, st.z], gas),
+        "cross lattice sources": ([gas.mass, gas.x, gas.y, gas.z], st),
         # ... some of which coincide with sources (a sampled subset of the gas as sources, halo_gas.py:307-321)
         "cross coincident": ([a[len(gas) // 6:5 * len(gas) // 6] for a in (gas.mass, gas.x, gas.y, gas.z)], gas),
     }
@@ -244,7 +246,10 @@ def test_large_calls_through_a_plan(monkeypatch):
         again = gpu(*src, tgt.x, tgt.y, tgt.z, "fast")
         assert np.array_equal(bits(again), bits(plan)), name           # bit-reproducible
         if name.startswith("cross"):
-            assert np.array_equal(bits(plan), bits(direct)), name      # not a block of the sources: same path
+            # HALMA_POT_PLAN_CROSS=0 keeps cross calls on the direct path
+            monkeypatch.setenv("HALMA_POT_PLAN_CROSS", "0")
+            assert np.array_equal(bits(gpu(*src, tgt.x, tgt.y, tgt.z, "fast")), bits(direct)), name
+            monkeypatch.delenv("HALMA_POT_PLAN_CROSS")
         # EXACT mode never takes the plan path
         if name == "block last":
             assert np.array_equal(bits(gpu(*src, tgt.x, tgt.y, tgt.z, "exact")), bits(ora(*src, tgt.x, tgt.y, tgt.z, "f32seq")))

@@ -212,6 +212,34 @@ def test_catalogue_with_external_groups_exact():
         assert np.array_equal(res.halo_mask(h), o.mask), h
         assert np.array_equal(res.be32[a:b].view(np.uint32), o.be32.view(np.uint32)), h
         assert res.halos[h].n_iter == o.n_iter
+    # the same job through the one-shot C entry point halma_unbind_catalogue (CSR offsets, host pointers)
+    import ctypes as C
+    L = _lib.lib()
+    cfg = _lib.UnbindConfig()
+    cfg.struct_size, cfg.mode, cfg.n_groups, cfg.n_pre, cfg.max_iter = C.sizeof(cfg), _lib.MODE_EXACT, 2, 1, 64
+    cfg.G, cfg.kappa, cfg.n_ranks = 4.3e-9, 4.0, 1
+    n, nh = int(off[-1]), len(sizes)
+    mem64 = [np.ascontiguousarray(a, np.float64) for a in mem]
+    geo = [np.ascontiguousarray(g[0], np.int64) for g in groups]
+    gcols = [[np.ascontiguousarray(g[k], np.float64) for g in groups] for k in range(1, 5)]
+    tbl = lambda arrs, T: (T * len(arrs))(*[a.ctypes.data_as(T) for a in arrs])      # noqa: E731
+    I64P, F64P = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    mask, be = np.zeros(n, np.uint8), np.zeros(n, np.float32)
+    en, idx = np.zeros(n, np.float64), np.zeros(n, np.int32)
+    hr = (_lib.HaloResult * nh)()
+    st = _lib.RunStats()
+    L.halma_unbind_catalogue.argtypes = None
+    rc = L.halma_unbind_catalogue(C.byref(cfg), C.c_int64(nh), off.ctypes.data_as(I64P),
+                                  *[a.ctypes.data_as(F64P) for a in mem64], tbl(geo, I64P),
+                                  tbl(gcols[0], F64P), tbl(gcols[1], F64P), tbl(gcols[2], F64P), tbl(gcols[3], F64P),
+                                  None, None, C.c_double(0.0), mask.ctypes.data_as(C.c_void_p),
+                                  be.ctypes.data_as(C.c_void_p), en.ctypes.data_as(C.c_void_p),
+                                  idx.ctypes.data_as(C.c_void_p), hr, C.byref(st))
+    assert rc == 0, L.halma_last_error()
+    assert np.array_equal(mask, res.mask) and np.array_equal(be.view(np.uint32), res.be32.view(np.uint32))
+    assert np.array_equal(en, res.energy) and np.array_equal(idx, res.idx_packed)
+    assert [hr[h].n_bound for h in range(nh)] == [res.halos[h].n_bound for h in range(nh)]
+    assert st.pairs == res.stats.pairs and st.passes == res.stats.passes
 
 
 def test_idempotence_and_rerun():
@@ -404,6 +432,38 @@ def test_stellar_onepass_golden(golden_dir):
     finally:
         halo_gas.AMRgrid_to_particles = halo_gas_amr
     np.testing.assert_array_equal(bound, g["bound"])
+
+
+def test_reference_call_sequences_replayed_through_the_dropin(golden_dir, monkeypatch):
+    """Every kernel call the reference's RPS and most_bound_particle made on the golden cases (recorded with its
+    float32 inputs by tests/golden/make_golden.py::call_sequences while the reference's own Python ran), replayed in
+    order through the drop-in package exactly as the reference calls it -- `from fortran_modules import particle;
+    particle.particle.brute_force_binding_energy(ncores, ntotal, ..., ntest, ...)` -- in EXACT mode (HALMA_MODE):
+    every result must equal the recorded one bit for bit."""
+    import importlib
+    import sys
+    monkeypatch.setenv("HALMA_MODE", "exact")
+    monkeypatch.syspath_prepend(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin"))
+    for m in [k for k in sys.modules if k == "fortran_modules" or k.startswith("fortran_modules.")]:
+        monkeypatch.delitem(sys.modules, m)
+    particle = importlib.import_module("fortran_modules.particle")
+    g = np.load(os.path.join(golden_dir, "call_sequences.npz"))
+    n_checked = 0
+    for tag in ("rps_one_dm", "rps_two_dm", "rps_sampled"):
+        for part in ("rps", "mb"):
+            for k in range(int(g["%s_%s_n_calls" % (tag, part)])):
+                a = {n: g["%s_%s_call%d_%s" % (tag, part, k, n)] for n in ("tm", "tx", "ty", "tz", "sx", "sy", "sz", "be")}
+                out = particle.particle.brute_force_binding_energy(
+                    np.int32(8), np.int32(len(a["tm"])), a["tm"], a["tx"], a["ty"], a["tz"], np.int32(len(a["sx"])),
+                    a["sx"], a["sy"], a["sz"])
+                assert out.dtype == np.float32 and out.shape == a["be"].shape
+                assert np.array_equal(out.view(np.uint32), a["be"].view(np.uint32)), (tag, part, k)
+                ser = particle.particle.serial_brute_force_binding_energy(
+                    np.int32(len(a["tm"])), a["tm"], a["tx"], a["ty"], a["tz"], np.int32(len(a["sx"])), a["sx"], a["sy"],
+                    a["sz"])
+                assert np.array_equal(ser.view(np.uint32), a["be"].view(np.uint32)), (tag, part, k)
+                n_checked += 1
+    assert n_checked == 22
 
 
 # ---- BASELINE sizes: properties the domain offers, plus sampled oracle checks ----------------

@@ -75,3 +75,23 @@ def test_com_and_bulk_velocity_match_reference_numba(golden_dir):
     np.testing.assert_allclose([cx, cy, cz], g["com"], rtol=1e-13)
     np.testing.assert_allclose(vb, g["vb"], rtol=1e-12)
     np.testing.assert_allclose(M, g["M"], rtol=1e-14)
+
+
+def test_call_sequences_fixture_is_consistent_with_the_driver_fixtures(golden_dir):
+    """call_sequences.npz (kernel calls of the reference's drivers WITH their float32 inputs) against the oracle
+    kernel and against the per-driver fixtures written by the same reference run."""
+    g = np.load(os.path.join(golden_dir, "call_sequences.npz"))
+    n = 0
+    for tag in ("rps_one_dm", "rps_two_dm", "rps_sampled"):
+        drv = np.load(os.path.join(golden_dir, tag + ".npz"))
+        for part, pre in (("rps", ""), ("mb", "mb_")):
+            assert int(g["%s_%s_n_calls" % (tag, part)]) == int(drv[pre + "n_calls"])
+            for k in range(int(drv[pre + "n_calls"])):
+                a = [g["%s_%s_call%d_%s" % (tag, part, k, nm)] for nm in ("tm", "tx", "ty", "tz", "sx", "sy", "sz")]
+                be = g["%s_%s_call%d_be" % (tag, part, k)]
+                assert all(x.dtype == np.float32 for x in a) and len(a[0]) == int(drv["%scall%d_ntotal" % (pre, k)])
+                assert np.array_equal(be.view(np.uint32), drv["%scall%d_be" % (pre, k)].view(np.uint32))
+                out = O.brute_force_binding_energy(1, len(a[0]), *a[:4], len(a[4]), *a[4:])
+                assert np.array_equal(out.view(np.uint32), be.view(np.uint32))
+                n += 1
+    assert n == 22
