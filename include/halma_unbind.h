@@ -229,6 +229,9 @@ int halma_plan_upload_group(halma_plan *plan, int group, const double *mass, con
 int halma_plan_upload_temp(halma_plan *plan, const double *temp, double cold_T);
 /* vb: double[3*n_halo]; required when vb_fixed = 1. */
 int halma_plan_set_vb(halma_plan *plan, const double *vb);
+/* The uploads are asynchronous copies on the plan's stream; this waits for them (callers that pipeline several
+ * plans use it to keep one plan's upload from sharing the host link with the next one's). */
+int halma_plan_sync(halma_plan *plan);
 
 /* Split mode only: join an NCCL communicator.  unique_id is the 128-byte ncclUniqueId
  * made by rank 0 (halma_nccl_unique_id) and broadcast by the caller. */

@@ -23,7 +23,7 @@ EXPORTS = (
     "halma_last_error", "halma_abi_version", "halma_device_count", "halma_device_info",
     "halma_host_alloc", "halma_host_free", "halma_potential_f32", "halma_potential_workspace_bytes",
     "halma_potential_f32_dev", "halma_plan_create", "halma_plan_destroy", "halma_plan_upload_members",
-    "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_nccl_unique_id", "halma_plan_join", "halma_comm_create", "halma_comm_destroy", "halma_plan_use_comm",
+    "halma_plan_upload_group", "halma_plan_upload_temp", "halma_plan_set_vb", "halma_plan_sync", "halma_nccl_unique_id", "halma_plan_join", "halma_comm_create", "halma_comm_destroy", "halma_plan_use_comm",
     "halma_plan_run", "halma_plan_download", "halma_plan_debug_pass_ns", "halma_unbind_halo", "halma_unbind_catalogue", "halma_microbench",
     "halma_halo_shape_f32", "halma_sigma_projections_f32",
     "halma_snapshot_create", "halma_snapshot_destroy", "halma_snapshot_cells", "halma_snapshot_upload_patch",
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.halma_plan_upload_group.argtypes = [vp, i32, vp, vp, vp, vp]
     L.halma_plan_upload_temp.argtypes = [vp, vp, C.c_double]
     L.halma_plan_set_vb.argtypes = [vp, vp]
+    L.halma_plan_sync.argtypes = [vp]
     L.halma_nccl_unique_id.argtypes = [vp]
     L.halma_plan_join.argtypes = [vp, vp]
     L.halma_comm_create.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]

@@ -1107,6 +1107,15 @@ extern "C" int halma_plan_set_vb(halma_plan *P, const double *vb)
     return HALMA_OK;
 }
 
+// Blocks until everything enqueued on the plan's stream (uploads, a run) has completed.
+extern "C" int halma_plan_sync(halma_plan *P)
+{
+    if (!P) return fail(HALMA_ERR_INVALID, "null plan");
+    CU_TRY(cudaSetDevice(P->cfg.device));
+    CU_TRY(cudaStreamSynchronize(P->stream));
+    return HALMA_OK;
+}
+
 extern "C" int halma_plan_join(halma_plan *P, const void *unique_id_128)
 {
     if (!P || !unique_id_128) return fail(HALMA_ERR_INVALID, "null pointer");

@@ -50,12 +50,13 @@ __global__ void __launch_bounds__(256) k_ext_halo(const HaloDesc *halo, int n_ha
 }
 
 __global__ void __launch_bounds__(256) k_make_keys(const int32_t *src_halo, const float *mem_c, const float *ext_c,
-                                                   int64_t n_pad, int64_t n_tot, uint64_t *keys, uint32_t *ids)
+                                                   int64_t n_pad, int64_t n_tot, uint32_t n_halo, uint64_t *keys, uint32_t *ids)
 {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_tot;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int32_t h = src_halo[i];
-        uint64_t key = ~0ull;                       // padding slots sort to the end
+        // padding slots sort to the end: halo id one past the last (the sort looks at the bits that can differ only)
+        uint64_t key = (static_cast<uint64_t>(n_halo) << 32) | 0xffffffffull;
         if (h >= 0) {
             const float v = i < n_pad ? mem_c[i] : ext_c[i - n_pad];
             key = (static_cast<uint64_t>(static_cast<uint32_t>(h)) << 32) | canon_bits(v);
@@ -128,13 +129,14 @@ cudaError_t sorted_build_axis(const SortedBuild &b, int axis, cudaStream_t s)
     const float *ext_c = axis == 0 ? b.ext.x : axis == 1 ? b.ext.y : b.ext.z;
     const int blocks = static_cast<int>(std::min<int64_t>((b.n_tot + 255) / 256, 148 * 16));
     if (b.n_tot == 0) return cudaSuccess;
-    k_make_keys<<<blocks, 256, 0, s>>>(b.src_halo, mem_c, ext_c, b.n_pad, b.n_tot, b.keys_in, b.ids_in);
+    k_make_keys<<<blocks, 256, 0, s>>>(b.src_halo, mem_c, ext_c, b.n_pad, b.n_tot, static_cast<uint32_t>(b.n_halo), b.keys_in,
+                                       b.ids_in);
     size_t tb = b.temp_bytes;
     int end_bit = 32;
     while (end_bit < 64 && (static_cast<uint64_t>(b.n_halo) >> (end_bit - 32)) != 0) ++end_bit;
+    // 32 coordinate bits + the bits of the halo id (0 .. n_halo, n_halo = the padding): fewer radix passes than 64
     cudaError_t e = cub::DeviceRadixSort::SortPairs(b.temp, tb, b.keys_in, b.keys_out, b.ids_in, b.ids_out,
-                                                    static_cast<int>(b.n_tot), 0, 64, s);
-    (void)end_bit;      // all 64 bits are sorted so that the ~0 padding keys end up last
+                                                    static_cast<int>(b.n_tot), 0, end_bit, s);
     if (e != cudaSuccess) return e;
     // padding of the sorted copies: coordinates NaN (never equal to anything), mass 0, key ~0, slot -1
     const size_t NS = static_cast<size_t>(b.n_spad);

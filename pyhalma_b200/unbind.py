@@ -286,6 +286,10 @@ class UnbindPlan:
         self._keep.append([vb])
         _lib.check(self._L.halma_plan_set_vb(self._h, vb.ctypes.data))
 
+    def sync(self):
+        """Wait for the asynchronous uploads (and anything else) enqueued on the plan's stream."""
+        _lib.check(self._L.halma_plan_sync(self._h))
+
     def join(self, unique_id: bytes):
         _lib.ensure_nccl_path()
         buf = C.create_string_buffer(bytes(unique_id), 128)
@@ -408,15 +412,21 @@ def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (
         plan.close()
 
 
-def cost_cuts(offsets, ext_offsets, parts: int) -> list:
+def cost_cuts(offsets, ext_offsets, parts: int, taper: bool = False) -> list:
     """Halo indices that cut a catalogue into at most `parts` runs of consecutive haloes of about
-    equal cost N_h (N_h + N_ext,h): [0, ..., n_halo], strictly increasing."""
+    equal cost N_h (N_h + N_ext,h): [0, ..., n_halo], strictly increasing.  taper: the first and the last
+    run get half the cost of the others (the pipelined one-shot call cannot hide the first run's upload
+    nor the last run's download, so they are kept short)."""
     offsets = _i64(offsets)
     nh = len(offsets) - 1
     nmem = np.diff(offsets).astype(np.float64)
     next_ = sum((np.diff(_i64(e)).astype(np.float64) for e in ext_offsets), np.zeros(nh))
     cum = np.concatenate(([0.0], np.cumsum(nmem * (nmem + next_))))
-    cuts = [0] + [int(np.searchsorted(cum, cum[-1] * k / parts)) for k in range(1, parts)] + [nh]
+    w = np.ones(parts)
+    if taper and parts >= 3:
+        w[0] = w[-1] = 0.5
+    frac = np.cumsum(w) / w.sum()
+    cuts = [0] + [int(np.searchsorted(cum, cum[-1] * f)) for f in frac[:-1]] + [nh]
     return sorted(set(min(max(c, 0), nh) for c in cuts))
 
 
@@ -430,7 +440,7 @@ def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, s
     groups = [(_i64(g[0]),) + tuple(_f64(a) for a in g[1:]) for g in groups]
     vb = None if vb is None else np.ascontiguousarray(vb, dtype=np.float64).reshape(nh, 3)
     temp = None if temp is None else _f64(temp)
-    cuts = cost_cuts(offsets, [g[0] for g in groups], streams)
+    cuts = cost_cuts(offsets, [g[0] for g in groups], streams, taper=True)
     out_mask = _lib.pinned_empty(n, np.uint8)
     out_be = _lib.pinned_empty(n, np.float32)
     out_energy = _lib.pinned_empty(n, np.float64)
@@ -438,6 +448,12 @@ def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, s
     raw = (_lib.HaloResult * max(1, nh))()
     stats: list = [None] * (len(cuts) - 1)
     errors: list = []
+
+    # Uploads go over the host link one part at a time, in order: started together they would share it, and the
+    # first part's loop could not begin until a third of ALL uploads had landed.  A part's upload then overlaps
+    # the device loop of the part before it, its download the loop of the part after it.
+    turn = threading.Condition()
+    state = {"next": 0}
 
     def part(k):
         try:
@@ -448,19 +464,30 @@ def _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, s
                             split_classes=split_classes, vb_fixed=vb is not None, max_iter=max_iter, G=G, kappa=kappa,
                             device=device, symmetric=symmetric, cache_external=cache_external,
                             incremental=incremental) as plan:
-                plan.upload_members(*[m[o0:o1] for m in members])
-                for gi, g in enumerate(sub):
-                    plan.upload_group(gi, g[1], g[2], g[3], g[4])
-                if vb is not None:
-                    plan.set_vb(vb[a:b])
-                if temp is not None:
-                    plan.upload_temp(temp[o0:o1], cold_T)
+                with turn:
+                    turn.wait_for(lambda: state["next"] == k or errors)
+                try:
+                    plan.upload_members(*[m[o0:o1] for m in members])
+                    for gi, g in enumerate(sub):
+                        plan.upload_group(gi, g[1], g[2], g[3], g[4])
+                    if vb is not None:
+                        plan.set_vb(vb[a:b])
+                    if temp is not None:
+                        plan.upload_temp(temp[o0:o1], cold_T)
+                    plan.sync()
+                finally:
+                    with turn:
+                        state["next"] = k + 1
+                        turn.notify_all()
                 stats[k] = plan.run()
                 plan.download_into(out_mask.ctypes.data + o0, out_be.ctypes.data + 4 * o0,
                                    out_energy.ctypes.data + 8 * o0, out_idx.ctypes.data + 4 * o0,
                                    C.addressof(raw) + a * C.sizeof(_lib.HaloResult))
         except Exception as exc:          # re-raised in the caller's thread
             errors.append(exc)
+            with turn:
+                state["next"] = max(state["next"], k + 1)
+                turn.notify_all()
 
     threads = [threading.Thread(target=part, args=(k,)) for k in range(len(cuts) - 1)]
     for t in threads:

@@ -83,7 +83,8 @@ def rps_sequence(device=0):
 
 
 def main():
-    from pyhalma_b200 import particle
+    from pyhalma_b200 import particle as particle_mod
+    particle = particle_mod if hasattr(particle_mod, "particle") else __import__("pyhalma_b200.particle", fromlist=["particle"])
     s, g, _ = _case()
     cat = lambda k: f32(np.concatenate([getattr(g, k), getattr(s, k)]))       # noqa: E731
     S, G = _f32(s), _f32(g)

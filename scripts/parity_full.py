@@ -9,7 +9,7 @@ GPU-box minutes are better spent on the GPU:
 
   python scripts/parity_full.py oracle      CPU only: runs the oracle loops, caches the results under
                                             profiles/_parity_cache/ (git-ignored, travels to the GPU box)
-  python scripts/parity_full.py gpu         on a B200: runs the library with the shipped defaults (FAST: symmetric
+  python scripts/parity_full.py gpu [--out F]   on a B200: runs the library with the shipped defaults (FAST: symmetric
                                             self-term, cached external sums, incremental passes, persistent loop
                                             kernel) and in EXACT mode, compares, writes profiles/parity_r02.json
                                             (read by bench.py) and prints a markdown table
@@ -155,4 +155,5 @@ if __name__ == "__main__":
     if stage == "oracle":
         stage_oracle(tag, sizes)
     else:
-        sys.exit(stage_gpu(tag, sizes, os.path.join(ROOT, "profiles", "parity_r02%s.json" % tag)))
+        out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(ROOT, "profiles", "parity_r02%s.json" % tag)
+        sys.exit(stage_gpu(tag, sizes, out))

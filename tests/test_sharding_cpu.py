@@ -239,3 +239,5 @@ def test_cost_cuts_for_the_multi_stream_catalogue_path():
     # equal haloes split evenly
     off = np.arange(0, 1201, 100)
     assert cost_cuts(off, [], 4) == [0, 3, 6, 9, 12]
+    # tapered: the first and the last run carry half the cost of the others (short upload head / download tail)
+    assert cost_cuts(off, [], 4, taper=True) == [0, 2, 6, 10, 12] and cost_cuts(off, [], 2, taper=True) == cost_cuts(off, [], 2)
