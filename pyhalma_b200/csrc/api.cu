@@ -270,7 +270,7 @@ static int potential_dev(DeviceCtx *c, int mode, const float *sm, const float *s
         return HALMA_OK;
     }
     const int variant = potential_pick_variant((n_tgt + 127) / 128, n_src, c->sm_count * c->bps_fast[0] * (kPotentialBlock / 32),
-                                               0, false);
+                                               0, false, kMaxSplit, kMinSplitSources);
     const int group = potential_group_size(mode, variant);
     const int grid = c->sm_count * c->blocks(mode, variant);
     const int S = choose_split(mode, n_tgt, n_src, group, kNominalTickets);
@@ -496,6 +496,7 @@ struct halma_plan {
     DBuf<int4> d_sched;                   // scheduling records, in `order` space
     DBuf<double> d_phi_full;
     int fused_index = -1;                 // persistent loop kernel serving this plan (fused.cu), -1: none
+    int min_split_sources = kMinSplitSources;
     int driver_ran = HALMA_DRIVER_ENQUEUE;
     std::vector<cudaEvent_t> cev;         // split mode: 2 per pass around the potential collectives, 2 around the rest
     DBuf<double> d_hdbl;                  // per-halo doubles: M(1) vb(3) vb_next(3) com(3)
@@ -730,7 +731,11 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     CU_TRY(P->d_be.alloc(NU));
     CU_TRY(P->d_E.alloc(NU));
     CU_TRY(P->d_idx.alloc(NU));
-    const int planes = cfg.mode == HALMA_MODE_FAST ? kMaxSplit : 1;
+    // j-split planes: small plans (where one pass cannot fill the machine with 128-target tickets otherwise) may
+    // cut a halo's sources into up to 32 pieces of >= 512 sources; large ones into 8 pieces of >= 2048
+    const bool small_plan = P->n_user <= kChunkSmallMaxMembers;
+    const int planes = cfg.mode == HALMA_MODE_FAST ? (small_plan ? kMaxSplitSmall : kMaxSplit) : 1;
+    P->min_split_sources = small_plan ? kMinSplitSourcesSmall : kMinSplitSources;
     CU_TRY(P->d_phi.alloc(planes * NP));
     CU_TRY(P->d_st.alloc(1));
     CU_TRY(P->d_redo.alloc(nh));
@@ -855,13 +860,15 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
             max_n0 = std::max<int64_t>(max_n0, halo[h].n0);
         }
         P->variant = potential_pick_variant(g128, max_src, P->ctx->sm_count * P->ctx->bps_fast[0] * (kPotentialBlock / 32),
-                                            max_n0, cfg.symmetric != 0 && P->np && cfg.mode == HALMA_MODE_FAST);
+                                            max_n0, cfg.symmetric != 0 && P->np && cfg.mode == HALMA_MODE_FAST, planes,
+                                            P->min_split_sources);
     }
     L.group_size = potential_group_size(cfg.mode, P->variant);
     L.rank = cfg.rank;
     L.n_ranks = cfg.n_ranks;
     L.target_items = kNominalTickets;
     L.max_split = planes;
+    L.min_split_sources = P->min_split_sources;
     L.halo_redo = P->d_redo.p;
     L.np_enabled = P->np ? 1 : 0;
     L.redo_enabled = 0;      // set below, once the reuse options are known
@@ -1480,6 +1487,11 @@ extern "C" int halma_plan_debug_pass_ns(halma_plan *P, uint32_t *out48)
     LoopState hst;
     CU_TRY(cudaMemcpy(&hst, P->d_st.p, sizeof hst, cudaMemcpyDeviceToHost));
     memcpy(out48, hst.pass_ns, sizeof hst.pass_ns);
+    // tuning aid: how long the slowest warp spent in the energy phase (overwrites nothing the caller relies on: printed)
+    if (getenv("HALMA_DEBUG_PHASES"))
+        for (int k = 0; k < 16 && hst.dbg_e_end[k]; ++k)
+            fprintf(stderr, "pass %d: energy phase (slowest warp) %.1f us of energy+compaction %.1f us\n", k,
+                    (hst.dbg_e_end[k] - hst.dbg_phase_start[k]) * 1e-3, hst.pass_ns[k][1] * 1e-3);
     return HALMA_OK;
 }
 

@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const Pot
             }
         }
         lap(1);
+        if (clock && pass < 16) st->dbg_phase_start[pass] = t_last;
         energy_phase(lp, par, pass);
+        if ((threadIdx.x & 31) == 0 && pass < 16) atomicMax(&st->dbg_e_end[pass], globaltimer_ns());
         compact_phase(lp, par, pass, true);
         fence_proxy_async_global();
         grid.sync();

@@ -30,8 +30,11 @@ namespace halma {
 constexpr int kLT = 128;                 // threads per block of every loop kernel (= the potential kernel's)
 constexpr int kLW = kLT / 32;
 // members per lane and chunk = p.chunk / 32: 8 (256-member chunks) or, for small plans, 2 (64-member chunks)
-constexpr int kHoist = 2;                // rounds whose loads are in flight together
+constexpr int kHoist = 1;                // rounds whose loads are in flight together (registers: the persistent
+                                         // kernel holds these phases to the potential code's 80 registers)
+constexpr int kHoistC = 2;               // ... in the compaction, which needs few registers per member
 static_assert(kChunk % (32 * kHoist) == 0 && kChunkSmall % (32 * kHoist) == 0, "rounds come in groups");
+static_assert(kChunk % (32 * kHoistC) == 0 && kChunkSmall % (32 * kHoistC) == 0, "rounds come in groups");
 
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
@@ -391,55 +394,78 @@ __device__ __forceinline__ void energy_chunk(const LoopParams &p, int c, int h, 
     const bool ext_cached = p.cache_ext && hd.n_ext > 0 && p.ext_ok[h] && !redo && !inc;
     const bool corr = p.np_enabled && !redo && !inc;
     const double vb0 = p.hvb[3 * h + 0], vb1 = p.hvb[3 * h + 1], vb2 = p.hvb[3 * h + 2];
+    // software pipeline: the slot -> user index lookups of the NEXT group of rounds are issued before this
+    // group's loads, so that a group costs one memory latency, not two
+    int64_t g_next[kHoist];
+#pragma unroll
+    for (int r = 0; r < kHoist; ++r) {
+        const int q = p0 + r * 32 + lane;
+        g_next[r] = q < n ? p.widx[par][hd.poff + q] : hd.uoff;
+    }
 #pragma unroll 1
     for (int r0 = 0; r0 < (p.chunk >> 5); r0 += kHoist) {
         if (p0 + r0 * 32 >= n) break;
         bool ok[kHoist];
         int64_t gi[kHoist];
         double phi[kHoist], vx[kHoist], vy[kHoist], vz[kHoist], mm[kHoist], ee[kHoist];
+        double xx[kHoist], yy[kHoist], zz[kHoist];
 #pragma unroll
         for (int r = 0; r < kHoist; ++r) {
-            const int q = p0 + (r0 + r) * 32 + lane;
-            ok[r] = q < n;
-            gi[r] = ok[r] ? p.widx[par][hd.poff + q] : hd.uoff;
+            ok[r] = p0 + (r0 + r) * 32 + lane < n;
+            gi[r] = g_next[r];
+            const int qn = p0 + (r0 + kHoist + r) * 32 + lane;
+            g_next[r] = (r0 + kHoist < (p.chunk >> 5) && qn < n) ? p.widx[par][hd.poff + qn] : hd.uoff;
+        }
+        // loads only, unconditional per lane (clamped index) and selected by warp-uniform flags, so that the
+        // compiler can issue all of them before the first use: one memory latency per group of rounds
+        double l_part[kHoist], l_sym[kHoist], l_keep[kHoist], l_ext[kHoist], l_c0[kHoist], l_c1[kHoist], l_c2[kHoist];
+#pragma unroll
+        for (int r = 0; r < kHoist; ++r) {
+            const int64_t i = hd.poff + min(p0 + (r0 + r) * 32 + lane, n - 1);
+            const int64_t g = gi[r];
+            const int64_t slot = hd.poff + (g - hd.uoff);      // the member's original slot
+            l_part[r] = p.phi_part[i];
+            l_sym[r] = p.sym_enabled ? p.phi_sym[i] : 0.0;
+            l_keep[r] = inc ? p.phi_keep[slot] : 0.0;
+            l_ext[r] = ext_cached ? p.phi_ext[slot] : 0.0;
+            l_c0[r] = corr ? p.ax[0].corr[slot] : 0.0;
+            l_c1[r] = corr ? p.ax[1].corr[slot] : 0.0;
+            l_c2[r] = corr ? p.ax[2].corr[slot] : 0.0;
+            vx[r] = p.vx[g];
+            vy[r] = p.vy[g];
+            vz[r] = p.vz[g];
+            mm[r] = p.m64[g];
+            xx[r] = p.x64[g];          // (for the centre of mass of the survivors: most members are)
+            yy[r] = p.y64[g];
+            zz[r] = p.z64[g];
         }
 #pragma unroll
         for (int r = 0; r < kHoist; ++r) {
-            const int64_t i = hd.poff + p0 + (r0 + r) * 32 + lane;
-            const int64_t g = gi[r];
-            const int64_t slot = hd.poff + (g - hd.uoff);      // the member's original slot
-            phi[r] = vx[r] = vy[r] = vz[r] = mm[r] = ee[r] = 0.0;
-            if (ok[r]) {
-                // Phi: ascending sum of the j-split partials
-                double ph = p.phi_part[i];
-                for (int k = 1; k < S; ++k) ph += p.phi_part[static_cast<int64_t>(k) * p.n_pad + i];
+            const int64_t i = hd.poff + min(p0 + (r0 + r) * 32 + lane, n - 1);
+            const int64_t slot = hd.poff + (gi[r] - hd.uoff);
+            // Phi: ascending sum of the j-split partials
+            double ph = l_part[r];
+            for (int k = 1; k < S; ++k) ph += p.phi_part[static_cast<int64_t>(k) * p.n_pad + i];
+            ee[r] = 0.0;
+            if (inc) {
+                // incremental pass: the planes hold what the members removed by the previous pass contributed
+                // (reference predicate applied); take it out of the potential kept from that pass
+                ph = l_keep[r] - ph;
+            } else if (!redo) {
                 // the two-sided sums of this pass (the slot is cleared for the next one below)
-                const double ps = p.sym_enabled ? p.phi_sym[i] : 0.0;
-                if (inc) {
-                    // incremental pass: the planes hold what the members removed by the previous pass contributed
-                    // (reference predicate applied); take it out of the potential kept from that pass
-                    ph = p.phi_keep[slot] - ph;
-                } else if (!redo) {
-                    if (p.sym_enabled) ph += ps;
-                    if (ext_cached) {
-                        // sum over the external sources, evaluated by the first pass only (potential.cu)
-                        double e = p.phi_ext[slot];
-                        if (pass == 0)
-                            for (int k = 1; k < S; ++k) e += p.phi_ext[static_cast<int64_t>(k) * p.n_pad + slot];
-                        ee[r] = e;
-                        ph += e;
-                    }
-                    if (corr) {
-                        // predicate-free path: take out the pairs that share a coordinate (potential.cu)
-                        ph -= (p.ax[0].corr[slot] + p.ax[1].corr[slot]) + p.ax[2].corr[slot];
-                    }
+                if (p.sym_enabled) ph += l_sym[r];
+                if (ext_cached) {
+                    // sum over the external sources, evaluated by the first pass only (potential.cu)
+                    double e = l_ext[r];
+                    if (pass == 0)
+                        for (int k = 1; k < S; ++k) e += p.phi_ext[static_cast<int64_t>(k) * p.n_pad + slot];
+                    ee[r] = e;
+                    ph += e;
                 }
-                phi[r] = ph;
-                vx[r] = p.vx[g];
-                vy[r] = p.vy[g];
-                vz[r] = p.vz[g];
-                mm[r] = p.m64[g];
+                // predicate-free path: take out the pairs that share a coordinate (potential.cu)
+                if (corr) ph -= (l_c0[r] + l_c1[r]) + l_c2[r];
             }
+            phi[r] = ph;
         }
 #pragma unroll
         for (int r = 0; r < kHoist; ++r) {
@@ -492,9 +518,9 @@ __device__ __forceinline__ void energy_chunk(const LoopParams &p, int c, int h, 
                     s[1] += m * vx[r];
                     s[2] += m * vy[r];
                     s[3] += m * vz[r];
-                    s[4] += m * p.x64[g];
-                    s[5] += m * p.y64[g];
-                    s[6] += m * p.z64[g];
+                    s[4] += m * xx[r];
+                    s[5] += m * yy[r];
+                    s[6] += m * zz[r];
                 }
             }
             count += __popc(__ballot_sync(0xffffffffu, bound));
@@ -575,13 +601,13 @@ __device__ __forceinline__ void compact_phase(const LoopParams &p, int par, int 
         int before = __ldcg(&p.chunk_off[c]);                    // survivors before this round, whole halo
         const int inc_next = p.incr_enabled ? __ldcg(&p.incr[h]) : 0;
 #pragma unroll 1
-        for (int r0 = 0; r0 < (p.chunk >> 5); r0 += kHoist) {
+        for (int r0 = 0; r0 < (p.chunk >> 5); r0 += kHoistC) {
             if (p0 + r0 * 32 >= n) break;
-            int f[kHoist], inv[kHoist][3];
-            float vals[kHoist][4];
-            int32_t wid[kHoist];
+            int f[kHoistC], inv[kHoistC][3];
+            float vals[kHoistC][4];
+            int32_t wid[kHoistC];
 #pragma unroll
-            for (int r = 0; r < kHoist; ++r) {
+            for (int r = 0; r < kHoistC; ++r) {
                 const int q = p0 + (r0 + r) * 32 + lane;
                 const int64_t i = hd.poff + min(q, n - 1);
                 f[r] = (q < n) ? p.flag[i] : 0;
@@ -592,14 +618,14 @@ __device__ __forceinline__ void compact_phase(const LoopParams &p, int par, int 
                 wid[r] = p.widx[par][i];
             }
 #pragma unroll
-            for (int r = 0; r < kHoist; ++r) {
+            for (int r = 0; r < kHoistC; ++r) {
                 const int q = p0 + (r0 + r) * 32 + lane;
                 const int64_t slot = hd.poff + (wid[r] - hd.uoff);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) inv[r][a] = (p.np_enabled && q < n && !f[r]) ? p.ax[a].inv[slot] : 0;
             }
 #pragma unroll
-            for (int r = 0; r < kHoist; ++r) {
+            for (int r = 0; r < kHoistC; ++r) {
                 const int q = p0 + (r0 + r) * 32 + lane;
                 const unsigned ballot = __ballot_sync(0xffffffffu, f[r]);
                 const int dst = before + __popc(ballot & ((1u << lane) - 1u));
@@ -655,7 +681,7 @@ __device__ __forceinline__ int sched_items(const LoopParams &p, const int4 rec, 
     S = 1;
     if (n <= 0) return 0;
     const bool inc = rec.z != 0;
-    S = min(want, min(p.max_split, max(1, rec.y / kMinSplitSources)));
+    S = min(want, min(p.max_split, max(1, rec.y / p.min_split_sources)));
     int items = my_groups(n, p.group_size, p.rank, p.n_ranks) * S;
     // correction tickets: three axes x blocks of the (static) sorted member list
     if (p.np_enabled && !inc) items += 3 * my_groups(rec.w, p.group_size, p.rank, p.n_ranks);

@@ -13,6 +13,8 @@ constexpr int kChunkSmallMaxMembers = 1 << 18;
 constexpr int kChunkSums = 10;            // float64 sums kept per chunk
 constexpr int kMinSplitSources = 2048;    // never split a halo's sources into pieces below this
 constexpr int kMaxSplit = 8;              // planes of the partial-potential buffer
+constexpr int kMinSplitSourcesSmall = 512;    // ... both in small plans (<= kChunkSmallMaxMembers members)
+constexpr int kMaxSplitSmall = 32;
 constexpr int kNominalTickets = 32768;    // j-split aims at this many tickets per pass (machine-independent)
 
 struct LoopParams {
@@ -58,7 +60,7 @@ struct LoopParams {
     double *phi_part;                     // [kMaxSplit][n_pad]
     LoopState *st;
     float G32, kappa32;
-    int32_t vb_fixed, max_iter, mode, group_size, rank, n_ranks, target_items, max_split;
+    int32_t vb_fixed, max_iter, mode, group_size, rank, n_ranks, target_items, max_split, min_split_sources;
     // predicate-free FAST path (potential.cu): sorted copies + per-halo fallback flags
     SortedAxis ax[3];
     const float *ax_m0[3];                // pristine masses of the sorted copies

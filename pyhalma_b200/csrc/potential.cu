@@ -195,18 +195,20 @@ int forced_variant()
 int potential_num_variants() { return kNumVariants; }
 
 int potential_pick_variant(int64_t groups_of_128, int64_t max_sources, int resident_warps, int64_t max_members,
-                           bool symmetric)
+                           bool symmetric, int max_split, int min_split_sources)
 {
     if (forced_variant() >= 0) return forced_variant();
     // symmetric tickets need the 128-member tiles of the throughput shape and bring their own
     // parallelism (tiles^2 / 2 tile pairs in chunks of 2..32): worth it from 64 tiles on
     // (scripts/probes/midsize_probe.py)
     if (symmetric && max_members >= 64 * 128) return 0;
-    // tickets the throughput shape would have after the j-split (at most kMaxSplit = 8 ways,
-    // pieces of >= 2048 sources): if that cannot occupy the resident warps, use small tickets
-    int64_t split = max_sources / 2048;
-    split = split < 1 ? 1 : (split > 8 ? 8 : split);
-    return groups_of_128 * split < resident_warps ? 1 : 0;
+    // tickets the throughput shape would have after the j-split (at most max_split ways, pieces of
+    // >= min_split_sources sources): if that cannot occupy about half the resident warps, use small tickets.
+    // (Shape 1 has one target per lane: four times the tickets, but one shared-memory load per evaluation, which
+    // makes it LSU-bound at about a third of the throughput shape's rate -- scripts/cfg1_passes.py.)
+    int64_t split = max_sources / min_split_sources;
+    split = split < 1 ? 1 : (split > max_split ? max_split : split);
+    return 2 * groups_of_128 * split < resident_warps ? 1 : 0;
 }
 
 int potential_group_size(int mode, int variant)

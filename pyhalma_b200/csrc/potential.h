@@ -15,7 +15,7 @@ constexpr int kMaxVariants = 8;
 int potential_num_variants();
 // groups_of_128: sum over haloes of ceil(n_targets / 128); max_sources: largest source count.
 int potential_pick_variant(int64_t groups_of_128, int64_t max_sources, int resident_warps, int64_t max_members,
-                           bool symmetric);
+                           bool symmetric, int max_split, int min_split_sources);
 // Targets per work item (warp): 32 (EXACT) or 32 * T (FAST, T = targets per lane of the shape).
 int potential_group_size(int mode, int variant);
 // Sets the dynamic shared-memory attribute and returns resident blocks per SM.

@@ -1,16 +1,14 @@
 #!/bin/bash
+# Eight B200s of one box: split mode against one GPU and the oracle, the default bench line at N = 8 (cfg3 strong scaling
+# + the split_cfg4 sub-object), cfg5 at full size.   gpurun --gpus 8 --timeout 1500 -- 'bash scripts/gpu_scale8.sh'
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
-run() { # n workload port
-  if [ "$1" = "1" ]; then timeout 900 python bench.py --workload $2 --steps 3 --warmup 3 2>/dev/null | tail -1 > gpurun_out/scale_$2_n$1.json
-  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $3 bench.py --gpus $1 --workload $2 --steps 3 --warmup 3 2>/dev/null | grep '^{' | tail -1 > gpurun_out/scale_$2_n$1.json; fi
-  python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/scale_$2_n$1.json")); print("$2 n=$1 value %.0f ms/step %.1f e2e %.0f frac %.3f"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["roofline"]["frac"]))
-except Exception as e: print("$2 n=$1 FAILED", e)
-PY
-}
-run 8 cfg3 29541; run 4 cfg3 29542; run 2 cfg3 29543; run 1 cfg3 0
-run 8 cfg4 29544; run 1 cfg4 0
-run 8 cfg2 29545; run 4 cfg2 29546
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 \
+    scripts/split_check.py --giant 2000000 2>gpurun_out/split_check8.err | tee gpurun_out/split_check_n8.txt
+tail -2 gpurun_out/split_check8.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29562 \
+    bench.py --gpus 8 --steps 5 --warmup 3 2>gpurun_out/bench_n8.err | grep '^{' | tail -1 | tee gpurun_out/bench_default_n8.json | cut -c1-300
+tail -3 gpurun_out/bench_n8.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29563 \
+    bench.py --gpus 8 --workload cfg5 --steps 3 --warmup 3 --no-one-sided --e2e-steps 1 2>gpurun_out/bench_cfg5_n8.err | grep '^{' | tail -1 | tee gpurun_out/bench_cfg5_n8.json | cut -c1-300
+tail -3 gpurun_out/bench_cfg5_n8.err

@@ -25,6 +25,8 @@ def main():
     tot = {"mufu_rsq_thread": 0, "mufu_rsq_thread_pred_on": 0, "mufu_rsq_warp": 0, "all_warp": 0, "samples": 0}
     cls = {}
     for r in rows[1:]:
+        if r and r[0] == "Address":
+            break          # the next kernel of the report
         if len(r) < len(hdr) or not r[col["Source"]].strip():
             continue
         ins = r[col["Source"]].strip()
