@@ -503,6 +503,7 @@ struct halma_plan {
     DBuf<unsigned long long> d_pairs, d_evals;
     DBuf<double> d_phi_sym, d_symq;
     bool sym = false;
+    int sym_rows = 4;
     // external-sum cache and incremental passes (FAST predicate-free path, one GPU)
     bool cache_ext = false, incr = false;
     DBuf<double> d_phi_ext, d_phi_keep;
@@ -886,6 +887,14 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     }
     L.phi_sym = P->d_phi_sym.p;
     L.sym_enabled = P->sym ? 1 : 0;
+    {
+        // row members per lane of the symmetric tickets: 4 (one row tile), or pairs of row tiles with HALMA_SYM_ROWS=8
+        // (half the shared-memory traffic per evaluation, but 128 registers and 4 blocks per SM: measured 1-3 %
+        // slower on one 1e6 halo, cfg2 and cfg3, profiles/sym_rows_ab_r02.txt)
+        const char *e = getenv("HALMA_SYM_ROWS");
+        P->sym_rows = e && atoi(e) == 8 ? 8 : 4;
+    }
+    L.sym_rows = P->sym_rows;
     L.sym_ext = P->d_symq.p;
     L.sym_q = P->sym ? P->d_symq.p + nh : nullptr;
     // External-sum cache and incremental passes ride on the predicate-free path (whose sums are kept per
@@ -944,6 +953,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     Q.phi_sym = P->d_phi_sym.p;
     Q.sym_q = L.sym_q;
     Q.sym_enabled = P->sym ? 1 : 0;
+    Q.sym_rows = P->sym_rows;
     Q.phi_ext = L.phi_ext;
     Q.ext_ok = L.ext_ok;
     Q.cache_ext = L.cache_ext;
@@ -960,7 +970,7 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
         Q.src[3 + a] = F32Set{P->sax[a].x, P->sax[a].y, P->sax[a].z, P->sax[a].m};
     }
     // the persistent loop kernel, where one exists for this configuration (fused.cu)
-    P->fused_index = cfg.n_ranks == 1 ? fused_kernel_index(cfg.mode, P->variant, P->np, P->sym) : -1;
+    P->fused_index = cfg.n_ranks == 1 ? fused_kernel_index(cfg.mode, P->variant, P->np, P->sym ? P->sym_rows : 0) : -1;
     if (cfg.use_graph == HALMA_DRIVER_FUSED && P->fused_index < 0)
         return fail(HALMA_ERR_INVALID, "no persistent loop kernel for this plan (split mode or a tuning kernel shape)");
     return HALMA_OK;

@@ -42,7 +42,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 
 // T = 0: EXACT arithmetic; otherwise the FAST shape with T targets per lane.
-template <int T, int MINB, bool NP, bool SYM>
+template <int T, int MINB, bool NP, int SYM>
 __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const PotParams pp, const LoopParams lp,
                                                                         const int do_pack)
 {
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const Pot
             if (*reinterpret_cast<volatile int32_t *>(&st->redo_any)) {
                 // haloes whose predicate-free sums came out non-finite, or whose incremental pass removed too
                 // much of some member's potential, are recomputed in full with the predicate
-                potential_pass_fast<T, false, false, false>(pp, rg, col, true);
+                potential_pass_fast<T, false, 0, false>(pp, rg, col, true);
                 grid.sync();
             }
         }
@@ -158,23 +158,25 @@ struct FusedEntry {
 
 // index: see fused_kernel_index()
 FusedEntry g_fused[] = {
-    {k_unbind_loop<0, 4, false, false>, 0},      // EXACT
-    {k_unbind_loop<4, 6, false, false>, 0},      // FAST predicated, throughput shape (shape 0)
-    {k_unbind_loop<1, 8, false, false>, 0},      // FAST predicated, small-halo shape (shape 1)
-    {k_unbind_loop<4, 6, true, false>, 0},       // FAST predicate-free, shape 0
-    {k_unbind_loop<1, 8, true, false>, 0},       // FAST predicate-free, shape 1
-    {k_unbind_loop<4, 6, true, true>, 0},        // FAST predicate-free + symmetric self-term, shape 0
+    {k_unbind_loop<0, 4, false, 0>, 0},      // EXACT
+    {k_unbind_loop<4, 6, false, 0>, 0},      // FAST predicated, throughput shape (shape 0)
+    {k_unbind_loop<1, 8, false, 0>, 0},      // FAST predicated, small-halo shape (shape 1)
+    {k_unbind_loop<4, 6, true, 0>, 0},       // FAST predicate-free, shape 0
+    {k_unbind_loop<1, 8, true, 0>, 0},       // FAST predicate-free, shape 1
+    {k_unbind_loop<4, 6, true, 4>, 0},       // FAST predicate-free + symmetric self-term (4 row members per lane), shape 0
+    {k_unbind_loop<4, 4, true, 8>, 0},       // ... with 8 row members per lane (pairs of row tiles)
 };
 constexpr int kNumFused = sizeof(g_fused) / sizeof(g_fused[0]);
 
 }  // namespace
 
-int fused_kernel_index(int mode, int variant, bool np, bool sym)
+int fused_kernel_index(int mode, int variant, bool np, int sym_rows)
 {
+    const bool sym = sym_rows != 0;
     if (mode == HALMA_MODE_EXACT) return 0;
     if (variant != 0 && variant != 1) return -1;      // tuning shapes exist as stand-alone kernels only
     if (!np) return 1 + variant;
-    if (sym) return variant == 0 ? 5 : -1;
+    if (sym) return variant == 0 ? (sym_rows == 8 ? 6 : 5) : -1;
     return 3 + variant;
 }
 

@@ -8,7 +8,7 @@
 namespace halma {
 
 // Which persistent kernel serves a plan, or -1 (tuning shapes and split mode use the multi-launch drivers).
-int fused_kernel_index(int mode, int variant, bool np, bool sym);
+int fused_kernel_index(int mode, int variant, bool np, int sym_rows);      // sym_rows: 0, 4 or 8
 // Shared-memory attribute and resident blocks per SM of every persistent kernel (once per device).
 cudaError_t fused_configure();
 int fused_blocks_per_sm(int index);

@@ -688,7 +688,7 @@ __device__ __forceinline__ int sched_items(const LoopParams &p, const int4 rec, 
     // symmetric tickets: row tiles x chunks of column tiles
     if (p.sym_enabled && !inc) {
         const int tiles = (n + p.group_size - 1) / p.group_size;
-        if (tiles >= 2) items += tiles * ((tiles - 1 + sym_chunk - 1) / sym_chunk);
+        if (tiles >= 2) items += sym_units(tiles, p.sym_rows) * ((tiles - 1 + sym_chunk - 1) / sym_chunk);
     }
     return items;
 }

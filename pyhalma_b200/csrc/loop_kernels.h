@@ -71,6 +71,7 @@ struct LoopParams {
     // symmetric self-term (potential.cu::sym_ticket): off-diagonal member x member sums
     double *phi_sym;                      // [n_pad]; the energy step clears what it read
     int32_t sym_enabled;
+    int32_t sym_rows;                     // row members per lane of the symmetric tickets (4 or 8), as in PotParams
     double *sym_ext;                      // [n_halo] largest coordinate extent of the halo's members
     double *sym_q;                        // [n_halo] quantum of the symmetric sums for the coming pass
     // external-sum cache (potential.cu, main tickets): first-pass sums over the external sources

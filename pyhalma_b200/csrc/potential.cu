@@ -54,7 +54,7 @@ namespace halma {
 // Stand-alone kernels: one launch = one potential pass (the multi-launch drivers and the f2py-level call).
 // fused.cu runs the same pass functions inside the persistent loop kernel.
 // ---------------------------------------------------------------------------------------
-template <int T, int MINB, bool NP, bool SYM = false, bool REUSE = false>
+template <int T, int MINB, bool NP, int SYM = 0, bool REUSE = false>
 __global__ void __launch_bounds__(kPotentialBlock, MINB) k_potential_fast(const PotParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -150,8 +150,8 @@ struct FastVariant {
 };
 
 #define HALMA_VARIANT(T, B) \
-    {T, B, k_potential_fast<T, B, false>, k_potential_fast<T, B, true>, k_potential_fast<T, B, true, false, true>, \
-     k_potential_fast<T, B, false, false, true>}
+    {T, B, k_potential_fast<T, B, false>, k_potential_fast<T, B, true>, k_potential_fast<T, B, true, 0, true>, \
+     k_potential_fast<T, B, false, 0, true>}
 const FastVariant kVariants[] = {
     HALMA_VARIANT(4, 6), HALMA_VARIANT(1, 8), HALMA_VARIANT(2, 8), HALMA_VARIANT(4, 4),
     HALMA_VARIANT(3, 6), HALMA_VARIANT(6, 3), HALMA_VARIANT(8, 3),
@@ -159,13 +159,14 @@ const FastVariant kVariants[] = {
 #undef HALMA_VARIANT
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-// The kernel that also runs the symmetric tickets.  6 resident blocks per SM (80 registers, a few
-// spill slots outside the hot loop) beat 5 and 4 by 2-5 % (profiles/np_variants_r01.txt).
+// The kernels that also run the symmetric tickets.  4 row members per lane: 6 resident blocks per SM (80 registers, a
+// few spill slots outside the hot loop) beat 5 and 4 by 2-5 % (profiles/np_variants_r01.txt).  8 row members per
+// lane (pairs of row tiles): 4 blocks per SM at 128 registers.
 typedef void (*SymKernel)(const PotParams);
-const SymKernel kSymKernels[3] = {k_potential_fast<4, 4, true, true>, k_potential_fast<4, 5, true, true>,
-                                  k_potential_fast<4, 6, true, true>};
-const SymKernel kSymReuseKernels[3] = {k_potential_fast<4, 4, true, true, true>, k_potential_fast<4, 5, true, true, true>,
-                                       k_potential_fast<4, 6, true, true, true>};
+const SymKernel kSymKernels[4] = {k_potential_fast<4, 4, true, 4>, k_potential_fast<4, 5, true, 4>,
+                                  k_potential_fast<4, 6, true, 4>, k_potential_fast<4, 4, true, 8>};
+const SymKernel kSymReuseKernels[4] = {k_potential_fast<4, 4, true, 4, true>, k_potential_fast<4, 5, true, 4, true>,
+                                       k_potential_fast<4, 6, true, 4, true>, k_potential_fast<4, 4, true, 8, true>};
 int sym_choice()
 {
     static int c = [] {
@@ -175,10 +176,8 @@ int sym_choice()
     }();
     return c;
 }
-#define kSymKernel kSymKernels[sym_choice()]
-#define kSymReuseKernel kSymReuseKernels[sym_choice()]
+int g_sym_bps[4] = {0, 0, 0, 0}, g_sym_reuse_bps[4] = {0, 0, 0, 0};
 int g_bps[16] = {0};
-int g_sym_bps = 0, g_sym_reuse_bps = 0;
 
 int forced_variant()
 {
@@ -249,13 +248,16 @@ cudaError_t potential_configure(int mode, int variant, int *blocks_per_sm)
     *blocks_per_sm = a < b ? a : b;
     if (variant < 16) g_bps[variant] = *blocks_per_sm;
     if (e == cudaSuccess && variant == 0) {
-        e = cudaFuncSetAttribute(kSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sym_bps, kSymKernel, kPotentialBlock, kSmemBytes);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kSymReuseKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sym_reuse_bps, kSymReuseKernel, kPotentialBlock, kSmemBytes);
+        for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
+            e = cudaFuncSetAttribute(kSymKernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+            if (e == cudaSuccess)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sym_bps[k], kSymKernels[k], kPotentialBlock, kSmemBytes);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(kSymReuseKernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+            if (e == cudaSuccess)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sym_reuse_bps[k], kSymReuseKernels[k], kPotentialBlock,
+                                                                  kSmemBytes);
+        }
     }
     return e;
 }
@@ -266,11 +268,13 @@ cudaError_t potential_launch(const PotParams &p, int mode, int variant, int grid
         k_potential_exact<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else if (p.np_enabled && !p.redo_only && p.sym_enabled) {
         const int per_sm = variant < 16 && g_bps[variant] > 0 ? g_bps[variant] : 1;
+        const int k = p.sym_rows == 8 ? 3 : sym_choice();
         if (p.cache_ext || p.incr_enabled)
-            kSymReuseKernel<<<grid_blocks / per_sm * (g_sym_reuse_bps > 0 ? g_sym_reuse_bps : 1), kPotentialBlock,
-                              kSmemBytes, stream>>>(p);
+            kSymReuseKernels[k]<<<grid_blocks / per_sm * (g_sym_reuse_bps[k] > 0 ? g_sym_reuse_bps[k] : 1), kPotentialBlock,
+                                  kSmemBytes, stream>>>(p);
         else
-            kSymKernel<<<grid_blocks / per_sm * (g_sym_bps > 0 ? g_sym_bps : 1), kPotentialBlock, kSmemBytes, stream>>>(p);
+            kSymKernels[k]<<<grid_blocks / per_sm * (g_sym_bps[k] > 0 ? g_sym_bps[k] : 1), kPotentialBlock, kSmemBytes,
+                             stream>>>(p);
     } else if (p.np_enabled && !p.redo_only && (p.cache_ext || p.incr_enabled))
         kVariants[variant].np_reuse<<<grid_blocks, kPotentialBlock, kSmemBytes, stream>>>(p);
     else if (p.np_enabled && !p.redo_only)

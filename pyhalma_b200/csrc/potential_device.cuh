@@ -194,15 +194,17 @@ __device__ __forceinline__ bool decode_ticket(const PotParams &p, int item, Tick
         return true;
     }
     if (!p.sym_enabled || groups < 2) return false;
-    // symmetric tickets: (row tile I, chunk c of the tiles J > I); ids of empty chunks are skipped
+    // symmetric tickets: (row unit u, chunk c of its column tiles); ids of empty chunks are skipped.  A row unit is
+    // one 128-member tile (sym_rows = 4 members per lane) or a pair of consecutive tiles (sym_rows = 8).
     local -= 3 * max(myblk, 0);
     const int ct = p.st->sym_chunk;
     const int chunks = (groups - 1 + ct - 1) / ct;
-    if (local >= groups * chunks) return false;
+    const int units = sym_units(groups, p.sym_rows);
+    if (local >= units * chunks) return false;
     t.corr_axis = 3;
     t.group = local / chunks;
     t.s = local % chunks;
-    return t.group % p.n_ranks == p.rank;      // split mode: row tiles are dealt round-robin like the target groups
+    return t.group % p.n_ranks == p.rank;      // split mode: row units are dealt round-robin like the target groups
 }
 
 // ---------------------------------------------------------------------------------------
@@ -375,8 +377,13 @@ __device__ __forceinline__ int64_t upper_bound_u32(const uint32_t *a, int64_t lo
     return lo;
 }
 
-// Correction ticket: 32*T consecutive members of the axis-sorted order against the range of
-// sorted sources whose key lies between the first and the last of them.
+// Correction ticket: 32*T consecutive members of the axis-sorted order against the sources that share their AXIS
+// coordinate.  Equal coordinates are equal keys (canonical bits), i.e. one contiguous run of the sorted copy around
+// the member.  Particles have short runs (positions cast to float32 in a cosmological box collide now and then),
+// lattice cells runs of a whole plane.  Short runs: every lane walks the runs of its own T members (a handful of
+// evaluations per member).  Long runs: the range of sorted sources between the first and the last member's key is
+// streamed through the ring against all 32*T members, 128 x (hi - lo) evaluations whatever the run lengths.
+constexpr int kCorrRunMax = 16;      // longest run the per-member walk takes
 template <int T, int AXIS>
 __device__ __forceinline__ void correction_ticket(const PotParams &p, const Ticket &tk, Ring &rg, int lane)
 {
@@ -385,29 +392,56 @@ __device__ __forceinline__ void correction_ticket(const PotParams &p, const Tick
     const SortedAxis &A = p.ax[AXIS];
     const int n0 = hd->n0;
     const int li0 = tk.group * kGroup;
+    const int64_t sb = hd->sbegin, se = hd->sbegin + n0 + hd->n_ext;
     float xi[T], yi[T], zi[T];
     int slot[T];
+    int jl[T], jr[T];          // the run of sources sharing member t's key (sorted positions fit 32 bits: tgt)
     double acc64[T];
+    bool longrun = false;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const int li = li0 + t * 32 + lane;
         const bool ok = li < n0;
-        const int64_t k = ok ? A.tgt[hd->uoff + li] : 0;
+        const int k = ok ? A.tgt[hd->uoff + li] : 0;
         xi[t] = ok ? A.x[k] : 0.f;
         yi[t] = ok ? A.y[k] : 0.f;
         zi[t] = ok ? A.z[k] : 0.f;
         slot[t] = ok ? A.slot[k] : -1;
         acc64[t] = 0.0;
+        jl[t] = jr[t] = k;
+        if (ok) {
+            const uint32_t key = A.key[k];
+            while (jl[t] > sb && A.key[jl[t] - 1] == key && k - jl[t] < kCorrRunMax) --jl[t];
+            while (jr[t] + 1 < se && A.key[jr[t] + 1] == key && jr[t] - k < kCorrRunMax) ++jr[t];
+            longrun |= k - jl[t] >= kCorrRunMax || jr[t] - k >= kCorrRunMax;
+        } else {
+            jr[t] = -1;      // an empty run
+        }
     }
-    const int64_t k_first = A.tgt[hd->uoff + li0];
-    const int64_t k_last = A.tgt[hd->uoff + min(li0 + kGroup, n0) - 1];
-    const int64_t sb = hd->sbegin, se = hd->sbegin + n0 + hd->n_ext;
-    int64_t lo = lower_bound_u32(A.key, sb, se, A.key[k_first]);
-    const int64_t hi = upper_bound_u32(A.key, sb, se, A.key[k_last]);
-    lo &= ~int64_t(3);       // 16-byte alignment for the bulk copies; sb is a multiple of 4
-    TileCursor cur;
-    cur.init_range(3 + AXIS, lo, static_cast<int>(hi - lo));
-    run_tiles<T, 2 + AXIS>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
+    if (!__any_sync(0xffffffffu, longrun)) {
+        const float kInf = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            float acc = 0.f;
+            uint64_t unused = 0ull;
+            for (int j = jl[t]; j <= jr[t]; ++j) {
+                // the member itself is in its run: zero separation, which every correction body skips; the second
+                // slot of the packed body is padding (infinitely far, massless)
+                pair_body<kCorrX + AXIS>(pack2(A.x[j], kInf), pack2(A.y[j], kInf), pack2(A.z[j], kInf), A.m[j], 0.f,
+                                         xi[t], yi[t], zi[t], acc, unused);
+            }
+            acc64[t] = static_cast<double>(acc);
+        }
+    } else {
+        const int64_t k_first = A.tgt[hd->uoff + li0];
+        const int64_t k_last = A.tgt[hd->uoff + min(li0 + kGroup, n0) - 1];
+        int64_t lo = lower_bound_u32(A.key, sb, se, A.key[k_first]);
+        const int64_t hi = upper_bound_u32(A.key, sb, se, A.key[k_last]);
+        lo &= ~int64_t(3);       // 16-byte alignment for the bulk copies; sb is a multiple of 4
+        TileCursor cur;
+        cur.init_range(3 + AXIS, lo, static_cast<int>(hi - lo));
+        run_tiles<T, 2 + AXIS>(p, cur, rg, lane, 0, 0, xi, yi, zi, acc64);
+    }
 #pragma unroll
     for (int t = 0; t < T; ++t)
         if (slot[t] >= 0) A.corr[slot[t]] = acc64[t];
@@ -425,9 +459,10 @@ __device__ __forceinline__ void correction_ticket(const PotParams &p, const Tick
 // inside whose window float64 addition is exact (sym_add), which keeps runs bit-reproducible.
 // scripts/probes/symmetric_probe.cu: 3.4-3.5 T pair evaluations/s = 6.8-7.1 T interactions/s.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void sym_tile(const float *__restrict__ stage, float *__restrict__ col, const float (&xi)[4],
-                                         const float (&yi)[4], const float (&zi)[4], const float (&mi)[4],
-                                         double (&acc64)[4], int lane)
+template <int TR>
+__device__ __forceinline__ void sym_tile(const float *__restrict__ stage, float *__restrict__ col, const float (&xi)[TR],
+                                         const float (&yi)[TR], const float (&zi)[TR], const float (&mi)[TR],
+                                         double (&acc64)[TR], int lane)
 {
     const uint64_t *X = reinterpret_cast<const uint64_t *>(stage);
     const uint64_t *Y = reinterpret_cast<const uint64_t *>(stage + kTileJ);
@@ -436,14 +471,16 @@ __device__ __forceinline__ void sym_tile(const float *__restrict__ stage, float 
     uint64_t *C2 = reinterpret_cast<uint64_t *>(col);
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {          // row partials: 32 terms per float32 sum, then float64
-        uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+        uint64_t acc2[TR];
+#pragma unroll
+        for (int t = 0; t < TR; ++t) acc2[t] = 0ull;
 #pragma unroll 2
         for (int k = half * 32; k < half * 32 + 32; ++k) {
             const int j = (k + lane) & (kTileJ / 2 - 1);
             const uint64_t x01 = X[j], y01 = Y[j], z01 = Z[j], m01 = M[j];
-            uint64_t c2 = 0ull;
+            uint64_t c2 = C2[j];          // the column pair's running sums: the first accumulate below adds to them
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < TR; ++t) {
                 const uint64_t dx = sub2(x01, pack2(xi[t], xi[t]));
                 const uint64_t dy = sub2(y01, pack2(yi[t], yi[t]));
                 const uint64_t dz = sub2(z01, pack2(zi[t], zi[t]));
@@ -454,14 +491,11 @@ __device__ __forceinline__ void sym_tile(const float *__restrict__ stage, float 
                 acc2[t] = fma2(m01, inv, acc2[t]);
                 c2 = fma2(pack2(mi[t], mi[t]), inv, c2);
             }
-            float c_lo, c_hi, o_lo, o_hi;
-            unpack2(c2, c_lo, c_hi);
-            unpack2(C2[j], o_lo, o_hi);
-            C2[j] = pack2(o_lo + c_lo, o_hi + c_hi);
+            C2[j] = c2;
             __syncwarp();          // the next step hands pair j to the neighbouring lane
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < TR; ++t) {
             float lo, hi;
             unpack2(acc2[t], lo, hi);
             acc64[t] += static_cast<double>(lo + hi);
@@ -482,33 +516,52 @@ __device__ __forceinline__ bool sym_add(double *dst, double v, double q, double 
     return false;
 }
 
+// TR = 4: the row unit is tile tk.group, columns are the tiles after it.  TR = 8: the row unit is a PAIR of tiles
+// (2u, 2u + 1) held as 8 members per lane -- half the shared-memory and bookkeeping instructions per evaluation --
+// or the single last row tile; chunk 0 of a pair first takes the pairs between its own two tiles (tile 2u + 1 as a
+// column, with the rows of that tile masked out: far away and massless, which contributes exactly zero).
+template <int TR>
 __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk, Ring &rg, float *col, int lane,
                                            int parity)
 {
     const HaloDesc *hd = &p.halo[tk.h];
     const int n = tk.n_tgt;
     const int G = (n + kTileJ - 1) / kTileJ;
-    const int I = tk.group;
     const int ct = p.st->sym_chunk;
-    const int j0 = I + 1 + tk.s * ct;
-    if (j0 >= G) return;                              // an empty chunk of this row
+    int I0, jfirst;
+    bool pair = false;
+    if (TR == 8) {
+        const int P = (G - 1) >> 1;
+        pair = tk.group < P;
+        I0 = pair ? 2 * tk.group : G - 2;
+        jfirst = pair ? I0 + 2 : G - 1;
+    } else {
+        I0 = tk.group;
+        jfirst = I0 + 1;
+    }
+    const bool intra = TR == 8 && pair && tk.s == 0;      // this ticket also does tile I0 x tile I0 + 1
+    int j0 = jfirst + tk.s * ct;
     const int j1 = min(j0 + ct, G);
+    if (intra) j0 = I0 + 1;                               // ... which sits right in front of its first column tile
+    if (j0 >= G) return;                                  // an empty chunk of this row unit
     const F32Set sp = p.src[parity];
     const int64_t base = hd->poff;
-    float xi[4], yi[4], zi[4], mi[4];
-    double acc64[4];
+    constexpr float kFar = 1e30f;      // (x - 1e30)^2 overflows to +inf, rsqrt(+inf) = +0: a masked row adds nothing
+    float xi[TR], yi[TR], zi[TR], mi[TR];
+    double acc64[TR];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {                     // row tile I < G - 1 is always full
-        const int64_t i = base + I * kTileJ + t * 32 + lane;
-        xi[t] = sp.x[i];
-        yi[t] = sp.y[i];
-        zi[t] = sp.z[i];
-        mi[t] = sp.m[i];
+    for (int t = 0; t < TR; ++t) {                        // row tiles are tiles < G - 1: always full
+        const int64_t i = base + static_cast<int64_t>(I0 + (t >> 2)) * kTileJ + (t & 3) * 32 + lane;
+        const bool live = t < 4 || (pair && !intra);
+        xi[t] = live ? sp.x[i] : kFar;
+        yi[t] = live ? sp.y[i] : kFar;
+        zi[t] = live ? sp.z[i] : kFar;
+        mi[t] = live ? sp.m[i] : 0.f;
         acc64[t] = 0.0;
     }
-    bool bad = false;
+    bool bad = false, first = true;
     // addends are rounded to multiples of q; while every running sum stays inside +-2^52 q the float64
-    // additions are exact and their order does not matter (loop_kernels.cu::k_halo_decide)
+    // additions are exact and their order does not matter (loop_device.cuh::decide_halo)
     // (split mode: every rank keeps to its share of the window, so the all-reduced total fits too)
     const double q = p.sym_q[tk.h], inv_q = q > 0.0 ? 1.0 / q : 0.0, window = ldexp(q, 52) / p.n_ranks;
     TileCursor prod;
@@ -545,8 +598,20 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
 #pragma unroll
         for (int e = lane; e < kTileJ; e += 32) col[e] = 0.f;
         __syncwarp();
-        sym_tile(stage, col, xi, yi, zi, mi, acc64, lane);
+        sym_tile<TR>(stage, col, xi, yi, zi, mi, acc64, lane);
         __syncwarp();
+        if (TR == 8 && intra && first) {
+            // the pairs inside the row unit are done: its second tile joins the rows for the remaining columns
+#pragma unroll
+            for (int t = 4; t < TR; ++t) {
+                const int64_t i = base + static_cast<int64_t>(I0 + 1) * kTileJ + (t & 3) * 32 + lane;
+                xi[t] = sp.x[i];
+                yi[t] = sp.y[i];
+                zi[t] = sp.z[i];
+                mi[t] = sp.m[i];
+            }
+        }
+        first = false;
         const int64_t tile0 = cons.base + cons.pos;
 #pragma unroll
         for (int e = lane; e < kTileJ; e += 32)
@@ -560,9 +625,11 @@ __device__ __forceinline__ void sym_ticket(const PotParams &p, const Ticket &tk,
         cons.next();
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < TR; ++t) {
+        if (t >= 4 && !pair) continue;                    // masked rows of a single-tile unit
         bad |= !(fabs(acc64[t]) <= 1.7976931348623157e308);
-        bad |= sym_add(&p.phi_sym[base + I * kTileJ + t * 32 + lane], acc64[t], q, inv_q, window);
+        bad |= sym_add(&p.phi_sym[base + static_cast<int64_t>(I0 + (t >> 2)) * kTileJ + (t & 3) * 32 + lane], acc64[t], q,
+                       inv_q, window);
     }
     // a zero separation between different tiles (exact duplicates) or non-finite input: the
     // predicated kernel recomputes the halo from scratch and phi_sym is ignored for it
@@ -593,12 +660,13 @@ __device__ __forceinline__ void warp_ring_setup(unsigned char *smem_raw, Ring &r
 // REUSE: the instantiations that know about the external-sum cache and the incremental passes; plans
 // without them run the REUSE = false kernels, whose code is what it was before those existed.
 // redo_only: the predicated re-evaluation of the haloes the predicate-free pass flagged.
-template <int T, bool NP, bool SYM, bool REUSE>
+// SYM: 0 = no symmetric tickets, 4 / 8 = symmetric tickets with that many row members per lane.
+template <int T, bool NP, int SYM, bool REUSE>
 __device__ __forceinline__ void potential_pass_fast(const PotParams &p, Ring &rg, float *col, const bool redo_only)
 {
     const LoopState *st = p.st;
     const int lane = threadIdx.x & 31;
-    static_assert(!SYM || (NP && T == 4), "symmetric tickets use 128-member tiles on the predicate-free kernel");
+    static_assert(SYM == 0 || ((SYM == 4 || SYM == 8) && NP && T == 4), "symmetric tickets use 128-member tiles on the predicate-free kernel");
 
     const int n_items = st->n_items;
     const int parity = st->parity;
@@ -613,7 +681,7 @@ __device__ __forceinline__ void potential_pass_fast(const PotParams &p, Ring &rg
         Ticket tk;
         if (!decode_ticket<kGroup>(p, item, tk)) continue;
         if (tk.corr_axis == 3) {
-            if (SYM) sym_ticket(p, tk, rg, col, lane, parity);
+            if constexpr (SYM != 0) sym_ticket<SYM>(p, tk, rg, col, lane, parity);
             continue;
         }
         if (tk.corr_axis >= 0) {

@@ -112,6 +112,36 @@ def test_gas_layout_fast_lattice_exclusions():
     assert first.size == 0 or first.max() < FAST_RTOL          # particles removed in earlier passes too
 
 
+def test_coordinate_sharing_runs_of_every_length_fast(monkeypatch):
+    monkeypatch.setenv("HALMA_NP_MIN_PAIRS", "0")          # the predicate-free kernel + correction tickets, whatever the size
+    # Correction tickets walk short runs of equal keys per member and stream long ones through the ring
+    # (potential_device.cuh::kCorrRunMax = 16 each side): runs of 2 .. 40 members sharing x, y or z, some of them
+    # together with external sources, straddle both paths and the switch between them inside one ticket.
+    rng = np.random.default_rng(31)
+    p = synth.plummer_stars(2600, 3e-3, 1e6, rng, centre=(11.0, -7.0, 3.0), bulk_v=(0., 0., 0.))
+    d = synth.plummer_stars(500, 6e-3, 4e6, rng, centre=(11.0, -7.0, 3.0), bulk_v=(0., 0., 0.))
+    free = rng.permutation(len(p))
+    used = 0
+    for k, length in enumerate((2, 3, 5, 15, 16, 17, 18, 31, 33, 34, 40, 2, 2, 3, 4, 9)):
+        members = free[used:used + length]
+        used += length
+        arr = (p.x, p.y, p.z)[k % 3]
+        arr[members] = arr[members[0]]
+        if k % 4 == 1:                      # externals that share the run's coordinate as well
+            ext = rng.choice(len(d), 3, replace=False)
+            (d.x, d.y, d.z)[k % 3][ext] = arr[members[0]]
+    kw = dict(post=[d.pos_mass()], kappa=9.0)
+    o = O.unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, variant="f64acc", **kw)
+    for sym in (True, False):
+        r = unbind_halo(p.x, p.y, p.z, p.vx, p.vy, p.vz, p.mass, mode="fast", symmetric=sym, **kw)
+        both = r.mask & o.mask
+        assert np.abs(r.be32[both].astype(np.float64) / o.be32[both] - 1).max() < FAST_RTOL
+        diff = r.mask != o.mask
+        assert np.all(O.energy_margin(o.energy, o.be32, 9.0)[diff] < BAND)
+        assert r.n_iter == o.n_iter or diff.any()
+        assert r.stats.evaluations < r.stats.pairs or not sym          # i.e. it did run the predicate-free path
+
+
 def test_exact_duplicates_and_signed_zero_fast():
     # exact duplicates far apart in index (different tiles) give zero separations the
     # predicate-free path cannot handle: the halo must be recomputed with the predicate.
