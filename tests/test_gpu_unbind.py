@@ -114,6 +114,7 @@ def test_gas_layout_fast_lattice_exclusions():
 
 def test_coordinate_sharing_runs_of_every_length_fast(monkeypatch):
     monkeypatch.setenv("HALMA_NP_MIN_PAIRS", "0")          # the predicate-free kernel + correction tickets, whatever the size
+    monkeypatch.setenv("HALMA_FAST_VARIANT", "0")          # ... in the throughput shape, which has the symmetric tickets
     # Correction tickets walk short runs of equal keys per member and stream long ones through the ring
     # (potential_device.cuh::kCorrRunMax = 16 each side): runs of 2 .. 40 members sharing x, y or z, some of them
     # together with external sources, straddle both paths and the switch between them inside one ticket.
