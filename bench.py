@@ -139,7 +139,7 @@ def shared_comm(rank, world, device):
 
 SYMMETRIC = True      # set from --symmetric
 REUSE = None          # set from --reuse: external-sum cache + incremental passes (None: the library default)
-E2E_STREAMS = 3       # parts of a catalogue in the one-shot (e2e) call, --e2e-streams
+E2E_STREAMS = 0       # parts of a catalogue in the one-shot (e2e) call, --e2e-streams (0: the library's choice)
 DRIVER = None         # set from --driver (None: the library default = the persistent loop kernel on one GPU)
 
 
@@ -363,7 +363,7 @@ def e2e_step(jobs_pinned, mode, device, rank=0, world=1):
     """One step through the public plan API from host buffers: create, H2D, run, D2H, destroy."""
     pairs = h2d = d2h = 0
     for job in jobs_pinned:
-        if job["kind"] == "catalogue" and E2E_STREAMS > 1:
+        if job["kind"] == "catalogue" and E2E_STREAMS != 1:
             # the one-shot catalogue call with its parts overlapped on separate streams / host threads
             from pyhalma_b200.unbind import unbind_catalogue
             kw = job["kw"]
@@ -383,6 +383,14 @@ def e2e_step(jobs_pinned, mode, device, rank=0, world=1):
         h2d += 7 * 8 * n + sum(4 * 8 * len(g[1]) for g in job["groups"])
         d2h += n * (1 + 4 + 8 + 4) + 80 * (len(job["offsets"]) - 1)
     return pairs, h2d, d2h
+
+
+def e2e_parts_note(jobs):
+    if E2E_STREAMS:
+        return str(E2E_STREAMS)
+    from pyhalma_b200.unbind import auto_parts
+    return "/".join(str(auto_parts(len(j["members"][0]), sum(len(g[1]) for g in j["groups"]))) for j in jobs
+                    if j["kind"] == "catalogue") + " (auto)"
 
 
 class Timed:
@@ -615,10 +623,10 @@ def run_gpu(args, rank, local_rank, world):
             "e2e": {"value": e2e_pairs_all / e2e_s_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d * reps,
                     "d2h_bytes_per_step": d2h * reps, "runs": e2e_steps, "ms_per_run": e2e_s_max / e2e_steps * 1e3,
                     "vs_resident": (e2e_pairs_all / e2e_s_max / 1e9) / value,
-                    "how": "public plan API per job (catalogue jobs: unbind_catalogue with %d overlapped parts), "
+                    "how": "public plan API per job (catalogue jobs: unbind_catalogue with %s overlapped parts), "
                            "everything inside the timing: plan create + H2D from pinned host + device loop + D2H of "
                            "mask, potentials, energies, member lists + destroy; bytes are per step = %d runs"
-                           % (E2E_STREAMS, reps)},
+                           % (e2e_parts_note(jobs), reps)},
             "gpu_launches": int(launches_all),
             "gpu_launches_note": "kernel launches of libhalma_unbind.so inside the timed region, all ranks; with the "
                                  "persistent loop kernel one launch is one complete unbinding",
@@ -774,8 +782,9 @@ def main():
                          "take less than --min-seconds; 1 for the other workloads)")
     ap.add_argument("--min-seconds", type=float, default=2.0, help="shortest timed region (cfg3)")
     ap.add_argument("--e2e-steps", type=int, default=8, help="runs of the end-to-end measurement")
-    ap.add_argument("--e2e-streams", type=int, default=3,
-                    help="catalogue workloads: parts of the one-shot call that overlap upload, sort and download")
+    ap.add_argument("--e2e-streams", type=int, default=0,
+                    help="catalogue workloads: parts of the one-shot call that overlap upload, sort and download "
+                         "(0: chosen by the library from the size of the upload, unbind.auto_parts)")
     ap.add_argument("--symmetric", type=int, default=1, choices=[0, 1],
                     help="evaluate member x member pairs once for both particles (FAST mode)")
     ap.add_argument("--reuse", type=int, default=None, choices=[0, 1],
@@ -798,7 +807,7 @@ def main():
     global SYMMETRIC, E2E_STREAMS, REUSE, DRIVER
     REUSE = None if args.reuse is None else bool(args.reuse)
     SYMMETRIC = bool(args.symmetric) and args.mode == "fast"
-    E2E_STREAMS = max(1, args.e2e_streams)
+    E2E_STREAMS = max(0, args.e2e_streams)
     DRIVER = args.driver
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -387,8 +387,11 @@ def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (
         overlap the device loop of another (haloes are independent; in FAST mode the j-split of a
         halo can differ from the one-plan run, i.e. potentials agree to ~1e-16 before their float32
         rounding rather than always bit for bit; EXACT mode is bit-identical).
+        0: chosen from the size of the upload (auto_parts).
     """
     offsets = _i64(offsets)
+    if streams == 0:
+        streams = auto_parts(int(offsets[-1]) if len(offsets) else 0, sum(len(g[1]) for g in groups))
     if streams > 1 and len(offsets) - 1 >= 2 * streams:
         return _unbind_catalogue_parts(offsets, x, y, z, vx, vy, vz, mass, groups, n_pre, split_classes, vb, kappa,
                                        max_iter, mode, device, G, temp, cold_T, symmetric, streams,
@@ -410,6 +413,16 @@ def unbind_catalogue(offsets, x, y, z, vx, vy, vz, mass, *, groups: Sequence = (
         return res
     finally:
         plan.close()
+
+
+def auto_parts(n_members: int, n_external: int = 0) -> int:
+    """Parts of the one-shot catalogue call.  A part more hides the upload of the parts behind it under the device loop
+    of the one before and costs ~1.2 ms of its own (plan, one-off sort launches, a loop launch, a download), so it pays
+    from ~3 ms of upload per part: 3 parts for the 9e6-member cfg3 catalogue on one GPU (507 MB, ~10 ms over PCIe:
+    47.8 ms against 55.8 ms in one plan), 1 for the eighth of it one GPU of eight gets (7.8 ms against 10.2 ms in
+    3 parts; scripts/e2e_share.py)."""
+    upload_ms = (56.0 * n_members + 32.0 * n_external) / 50e6          # float64 rows over ~50 GB/s
+    return max(1, min(3, 1 + int(upload_ms / 3.0)))
 
 
 def cost_cuts(offsets, ext_offsets, parts: int, taper: bool = False) -> list:

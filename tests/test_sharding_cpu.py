@@ -241,3 +241,13 @@ def test_cost_cuts_for_the_multi_stream_catalogue_path():
     assert cost_cuts(off, [], 4) == [0, 3, 6, 9, 12]
     # tapered: the first and the last run carry half the cost of the others (short upload head / download tail)
     assert cost_cuts(off, [], 4, taper=True) == [0, 2, 6, 10, 12] and cost_cuts(off, [], 2, taper=True) == cost_cuts(off, [], 2)
+
+
+def test_auto_parts_of_the_one_shot_catalogue_call():
+    from pyhalma_b200.unbind import auto_parts
+    assert auto_parts(0) == 1
+    assert auto_parts(1_110_367) == 1          # an eighth of cfg3: 62 MB, one plan
+    assert auto_parts(4_500_000) == 2
+    assert auto_parts(9_062_762) == 3          # the cfg3 catalogue on one GPU: 507 MB
+    assert auto_parts(10 ** 9) == 3            # never more: the parts' fixed costs add up
+    assert auto_parts(1_000_000, 6_000_000) >= auto_parts(1_000_000)
