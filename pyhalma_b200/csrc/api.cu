@@ -1502,6 +1502,13 @@ extern "C" int halma_plan_debug_pass_ns(halma_plan *P, uint32_t *out48)
         for (int k = 0; k < 16 && hst.dbg_e_end[k]; ++k)
             fprintf(stderr, "pass %d: energy phase (slowest warp) %.1f us of energy+compaction %.1f us\n", k,
                     (hst.dbg_e_end[k] - hst.dbg_phase_start[k]) * 1e-3, hst.pass_ns[k][1] * 1e-3);
+    if (getenv("HALMA_DEBUG_PHASES") && P->fused_index >= 0) {
+        const double warps = static_cast<double>(P->ctx->sm_count) * fused_blocks_per_sm(P->fused_index) * (kPotentialBlock / 32);
+        for (int k = 0; k < 16 && hst.dbg_pot_busy[k]; ++k)
+            fprintf(stderr, "pass %d: potential phase %.1f us, %u tickets, warps busy %.3f of it on average\n", k,
+                    hst.pass_ns[k][0] * 1e-3, hst.dbg_items[k],
+                    hst.dbg_pot_busy[k] / (warps * (hst.pass_ns[k][0] > 0 ? hst.pass_ns[k][0] : 1)));
+    }
     return HALMA_OK;
 }
 

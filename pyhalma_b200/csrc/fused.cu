@@ -94,10 +94,13 @@ __global__ void __launch_bounds__(kPotentialBlock, MINB) k_unbind_loop(const Pot
 
     // ---- passes ----
     while (*reinterpret_cast<volatile int32_t *>(&st->any_active)) {
+        const unsigned long long t_pot = (threadIdx.x & 31) == 0 ? globaltimer_ns() : 0ull;
+        if (clock && pass < 16) st->dbg_items[pass] = static_cast<unsigned int>(st->n_items);
         if constexpr (T == 0)
             potential_pass_exact(pp, rg);
         else
             potential_pass_fast<T, NP, SYM, true>(pp, rg, col, false);
+        if ((threadIdx.x & 31) == 0 && pass < 16) atomicAdd(&st->dbg_pot_busy[pass], globaltimer_ns() - t_pot);
         grid.sync();
         if constexpr (T != 0) {
             if (*reinterpret_cast<volatile int32_t *>(&st->redo_any)) {

@@ -32,6 +32,7 @@ constexpr int kLW = kLT / 32;
 // members per lane and chunk = p.chunk / 32: 8 (256-member chunks) or, for small plans, 2 (64-member chunks)
 constexpr int kHoist = 1;                // rounds whose loads are in flight together (registers: the persistent
                                          // kernel holds these phases to the potential code's 80 registers)
+constexpr int kIncPieceSources = 512;    // j-split piece of an incremental halo's removed members (sched_items)
 constexpr int kHoistC = 2;               // ... in the compaction, which needs few registers per member
 static_assert(kChunk % (32 * kHoist) == 0 && kChunkSmall % (32 * kHoist) == 0, "rounds come in groups");
 static_assert(kChunk % (32 * kHoistC) == 0 && kChunkSmall % (32 * kHoistC) == 0, "rounds come in groups");
@@ -682,13 +683,20 @@ __device__ __forceinline__ int sched_items(const LoopParams &p, const int4 rec, 
     if (n <= 0) return 0;
     const bool inc = rec.z != 0;
     S = min(want, min(p.max_split, max(1, rec.y / p.min_split_sources)));
+    // An incremental pass is short (survivors x removed), so a big halo's tickets -- 128 targets x all the members it
+    // removed -- can each last as long as the rest of the pass: where the pass has few tickets (want > 1), cut its
+    // removed list into pieces of ~kIncPieceSources (at least a tile).  (With plenty of tickets the extra pieces only
+    // cost: every piece loads its targets and kept potentials again.)
+    if (inc && want > 1) S = min(p.max_split, max(S, min(rec.y / kIncPieceSources, rec.y / 128)));
+    S = max(S, 1);
     int items = my_groups(n, p.group_size, p.rank, p.n_ranks) * S;
-    // correction tickets: three axes x blocks of the (static) sorted member list
-    if (p.np_enabled && !inc) items += 3 * my_groups(rec.w, p.group_size, p.rank, p.n_ranks);
+    // correction tickets: blocks of the (static) sorted member lists, the three axes in one ticket
+    if (p.np_enabled && !inc) items += my_groups(rec.w, p.group_size, p.rank, p.n_ranks);
     // symmetric tickets: row tiles x chunks of column tiles
     if (p.sym_enabled && !inc) {
         const int tiles = (n + p.group_size - 1) / p.group_size;
-        if (tiles >= 2) items += sym_units(tiles, p.sym_rows) * ((tiles - 1 + sym_chunk - 1) / sym_chunk);
+        const int ct = sym_chunk_of(sym_chunk, tiles);
+        if (tiles >= 2) items += sym_units(tiles, p.sym_rows) * ((tiles - 1 + ct - 1) / ct);
     }
     return items;
 }
