@@ -167,7 +167,7 @@ FusedEntry g_fused[] = {
     {k_unbind_loop<4, 6, true, 0>, 0},       // FAST predicate-free, shape 0
     {k_unbind_loop<1, 8, true, 0>, 0},       // FAST predicate-free, shape 1
     {k_unbind_loop<4, 6, true, 4>, 0},       // FAST predicate-free + symmetric self-term (4 row members per lane), shape 0
-    {k_unbind_loop<4, 4, true, 8>, 0},       // ... with 8 row members per lane (pairs of row tiles)
+    {k_unbind_loop<4, 5, true, 8>, 0},       // ... with 8 row members per lane (pairs of row tiles)
 };
 constexpr int kNumFused = sizeof(g_fused) / sizeof(g_fused[0]);
 

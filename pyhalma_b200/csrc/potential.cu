@@ -161,12 +161,12 @@ constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 // The kernels that also run the symmetric tickets.  4 row members per lane: 6 resident blocks per SM (80 registers, a
 // few spill slots outside the hot loop) beat 5 and 4 by 2-5 % (profiles/np_variants_r01.txt).  8 row members per
-// lane (pairs of row tiles): 4 blocks per SM at 128 registers.
+// lane (pairs of row tiles): 5 blocks per SM at 96 registers (6 would spill inside the rotation loop).
 typedef void (*SymKernel)(const PotParams);
 const SymKernel kSymKernels[4] = {k_potential_fast<4, 4, true, 4>, k_potential_fast<4, 5, true, 4>,
-                                  k_potential_fast<4, 6, true, 4>, k_potential_fast<4, 4, true, 8>};
+                                  k_potential_fast<4, 6, true, 4>, k_potential_fast<4, 5, true, 8>};
 const SymKernel kSymReuseKernels[4] = {k_potential_fast<4, 4, true, 4, true>, k_potential_fast<4, 5, true, 4, true>,
-                                       k_potential_fast<4, 6, true, 4, true>, k_potential_fast<4, 4, true, 8, true>};
+                                       k_potential_fast<4, 6, true, 4, true>, k_potential_fast<4, 5, true, 8, true>};
 int sym_choice()
 {
     static int c = [] {
