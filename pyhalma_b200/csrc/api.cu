@@ -57,7 +57,29 @@ struct DeviceCtx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     std::mutex mu;
+    // grow-only free list of small pinned buffers (the loop state a run reads back): cudaMallocHost synchronises the
+    // device, so a plan borrows one for the duration of a run instead of owning one
+    std::vector<void *> pinned_free;
+    std::mutex pinned_mu;
 };
+constexpr size_t kPinnedSlotBytes = 4096;
+static cudaError_t pinned_borrow(DeviceCtx *c, void **out)
+{
+    {
+        std::lock_guard<std::mutex> lock(c->pinned_mu);
+        if (!c->pinned_free.empty()) {
+            *out = c->pinned_free.back();
+            c->pinned_free.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaMallocHost(out, kPinnedSlotBytes);
+}
+static void pinned_return(DeviceCtx *c, void *p)
+{
+    std::lock_guard<std::mutex> lock(c->pinned_mu);
+    c->pinned_free.push_back(p);
+}
 
 static DeviceCtx g_ctx[64];
 static std::mutex g_ctx_mu;
@@ -1398,9 +1420,17 @@ extern "C" int halma_plan_run(halma_plan *P, halma_run_stats *stats)
         }
         CU_TRY(fused_launch(P->fused_index, P->pp, P->lp, do_pack, sm, s));
         ++launches;
-        CU_TRY(cudaMemcpyAsync(&hst, P->d_st.p, sizeof hst, cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaEventRecord(P->ev_stop, s));
-        CU_TRY(cudaStreamSynchronize(s));
+        // the loop state comes back through pinned memory, so that the copy and the stop event are queued behind the
+        // kernel without the host in between
+        static_assert(sizeof(LoopState) <= kPinnedSlotBytes, "pinned slot");
+        void *pin = nullptr;
+        CU_TRY(pinned_borrow(P->ctx, &pin));
+        cudaError_t ce = cudaMemcpyAsync(pin, P->d_st.p, sizeof hst, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaEventRecord(P->ev_stop, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce == cudaSuccess) memcpy(&hst, pin, sizeof hst);
+        pinned_return(P->ctx, pin);
+        CU_TRY(ce);
         passes = pot_launches = hst.pass;
     } else if (nh > 0) {
         CU_TRY(launch_pack_members(P->lp, sm, s));
