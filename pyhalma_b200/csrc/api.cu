@@ -911,20 +911,20 @@ static int plan_build(halma_plan *P, const int64_t *offsets, const int64_t *cons
     L.sym_enabled = P->sym ? 1 : 0;
     {
         // Row members per lane of the symmetric tickets: 4 (one row tile) or 8 (a pair of row tiles: half the
-        // shared-memory loads per evaluation, 6.0 instead of 6.75 issue slots per rsqrt, at 96 registers = 5 blocks
-        // per SM instead of 6).  8 wins where member x member pairs of ONE big halo are nearly all the work (one
-        // 1e6-star halo 163.6 -> 159.5 ms, the 2e6-star halo 697.6 -> 680.1 ms) and loses a little where the
-        // one-sided code -- external sources, many small haloes -- matters, which runs on the same blocks (cfg2
-        // stars +1.3 %, the cfg3 catalogue +0.3 %; profiles/sym_rows_ab_r02.txt).  The rule depends on the problem
-        // only, so a split run picks what the one-GPU run picks.  HALMA_SYM_ROWS=4|8 overrides it.
-        double self_pairs = 0.0, ext_pairs = 0.0, top = 0.0;
+        // shared-memory loads per evaluation and the next step's sources prefetched across the warp barrier, 5.9
+        // instead of 6.75 issue slots per rsqrt, at 96 registers = 5 blocks per SM instead of 6).  8 wins wherever
+        // the member x member pairs are a good part of the work (one 1e6-star pass 163.6 -> 156.2 ms, the cfg3
+        // catalogue 33.7 -> 33.3 ms, cfg2's gas 84.0 -> 82.4 ms) and loses a little where the one-sided code over
+        // external sources dominates, which runs on the same, fewer, blocks (cfg2's stars, 14 % member pairs: +0.8 %;
+        // profiles/sym_rows_ab_r02.txt): 8 from ~30 % of the evaluations on.  The rule depends on the problem only,
+        // so a split run picks what the one-GPU run picks.  HALMA_SYM_ROWS=4|8 overrides it.
+        double self_pairs = 0.0, ext_pairs = 0.0;
         for (int64_t h = 0; h < nh; ++h) {
             const double n0 = static_cast<double>(halo[h].n0);
             self_pairs += n0 * n0;
             ext_pairs += n0 * halo[h].n_ext;
-            top = std::max(top, n0);
         }
-        P->sym_rows = (top >= static_cast<double>(1 << 18) && top * top >= 0.9 * self_pairs && 8.0 * ext_pairs <= self_pairs) ? 8 : 4;
+        P->sym_rows = self_pairs >= 0.85 * ext_pairs ? 8 : 4;      // member pairs are evaluated once: n0^2 / 2 each
         if (const char *e = getenv("HALMA_SYM_ROWS")) P->sym_rows = atoi(e) == 8 ? 8 : (atoi(e) == 4 ? 4 : P->sym_rows);
     }
     L.sym_rows = P->sym_rows;
