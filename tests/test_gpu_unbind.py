@@ -682,6 +682,34 @@ def test_symmetric_self_term_against_one_sided_and_oracle():
     np.testing.assert_array_equal(sym.be32, one.be32)          # both took the same fallback
 
 
+@pytest.mark.parametrize("rows", ["4", "8"])
+def test_symmetric_row_units_of_4_and_8_members_per_lane(monkeypatch, rows):
+    """The symmetric tickets hold one row tile (4 members per lane) or a pair of row tiles (8) per warp; the library
+    picks by the share of member x member work (api.cu::plan_build), HALMA_SYM_ROWS forces either.  Both kernels on
+    a halo with an odd number of row tiles, a short last tile, external groups, coordinate-sharing pairs and more
+    than one pass: potentials within the FAST tolerance of the float64 oracle, masks identical outside the band."""
+    monkeypatch.setenv("HALMA_SYM_ROWS", rows)
+    monkeypatch.setenv("HALMA_NP_MIN_PAIRS", "0")
+    monkeypatch.setenv("HALMA_FAST_VARIANT", "0")
+    rng = np.random.default_rng(2024)
+    n = 128 * 9 + 57                                  # 10 tiles: 9 row tiles = 4 pairs + a single, short last column
+    st = synth.plummer_stars(n, 4 * synth.KPC, 1e6, rng, centre=(3.0, -2.0, 7.0), interloper_frac=0.2)
+    synth.add_coincident_pairs(st, 6, rng)
+    dm = synth.dm_cloud(700, 15 * synth.KPC, 1e7, rng, centre=(3.0, -2.0, 7.0))
+    kw = dict(post=[dm.pos_mass()], kappa=9.0)
+    args = (st.x, st.y, st.z, st.vx, st.vy, st.vz, st.mass)
+    o = O.unbind_halo(*args, variant="f64acc", **kw)
+    r = unbind_halo(*args, mode="fast", symmetric=True, **kw)
+    assert o.n_iter >= 2
+    assert r.stats.evaluations < r.stats.pairs          # the symmetric tickets did run
+    both = r.mask & o.mask
+    assert np.abs(r.be32[both].astype(np.float64) / o.be32[both] - 1).max() < FAST_RTOL
+    diff = r.mask != o.mask
+    assert np.all(O.energy_margin(o.energy, o.be32, 9.0)[diff] < BAND)
+    again = unbind_halo(*args, mode="fast", symmetric=True, **kw)
+    np.testing.assert_array_equal(again.be32.view(np.uint32), r.be32.view(np.uint32))      # bit-reproducible
+
+
 def test_symmetric_mode_forced_on_small_and_odd_inputs():
     """The same battery as the predicate-free path, with symmetric tickets on and the throughput
     shape forced so that small and ragged haloes go through them (haloes of <= 128 members have
