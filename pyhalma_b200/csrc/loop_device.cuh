@@ -682,7 +682,13 @@ __device__ __forceinline__ int sched_items(const LoopParams &p, const int4 rec, 
     S = 1;
     if (n <= 0) return 0;
     const bool inc = rec.z != 0;
-    S = min(want, min(p.max_split, max(1, rec.y / p.min_split_sources)));
+    // sources a main ticket streams: with the symmetric self-term only ONE tile of the members (its own) plus the
+    // externals -- the other member tiles belong to the symmetric tickets, and cutting them into j-split pieces only
+    // made empty tickets (60 % more tickets in the first pass of an eighth of the cfg3 catalogue, each fetched,
+    // decoded and stored as a plane of zeros that the energy step then added up)
+    int n_src = rec.y;
+    if (p.sym_enabled && !inc && n > p.group_size) n_src = rec.y - n + p.group_size;
+    S = min(want, min(p.max_split, max(1, n_src / p.min_split_sources)));
     // An incremental pass is short (survivors x removed), so a big halo's tickets -- 128 targets x all the members it
     // removed -- can each last as long as the rest of the pass: where the pass has few tickets (want > 1), cut its
     // removed list into pieces of ~kIncPieceSources (at least a tile).  (With plenty of tickets the extra pieces only
